@@ -1,0 +1,371 @@
+"""Pins the CPU oracle against the reference's OWN known-answer and invariant tests
+(SURVEY.md section 8c).  The reference ships no golden vectors and cannot run here (no
+Julia), so these ported tests are what earns the oracle its trust.  Each test cites the
+reference test it restates (paths relative to /root/reference/test).
+"""
+import numpy as np
+import pytest
+
+import cases
+
+
+@pytest.fixture(scope="module")
+def O(oracle):
+    return oracle
+
+
+# ---- test_minmod.jl:24-27 -----------------------------------------------------------------
+def test_minmod(O):
+    assert O.minmod(1, 2, 3) == 1
+    assert O.minmod(-1, -2, -3) == -1
+    assert O.minmod(1, -2, 3) == 0
+    got = [O.minmod(a, b, c) for a, b, c in zip([1, -2, -3], [3, -5, 2], [4, -3, 4])]
+    assert got == [1, -2, 0]
+
+
+# ---- test_bottom_topography.jl:37-54, 77-109 ------------------------------------------------
+def test_bottom_topography_constant(O):
+    for val in (0.0, 3.14):
+        s = O.OracleSim(dict(dim=1, nx=10, gc=2, B=val))
+        assert s.B_cell(45) == val and s.B_face_left(45, 12) == val and s.B_face_right(45) == val
+
+
+def test_bottom_topography_1d(O):
+    syn = cases.synthetic()
+    nx = 10
+    B = syn.cell_faces(nx, 2, 0.0, 10.0, interior=False)
+    assert B.shape == (nx + 5,)
+    s = O.OracleSim(dict(dim=1, nx=nx, gc=2, extent=[0.0, 10.0], B=B))
+    assert s.B_cell(4 + 2) == pytest.approx(3.5, abs=1e-10)
+    assert s.B_cell(7 + 2) == pytest.approx(6.5, abs=1e-10)
+    assert s.B_face_right(4 + 2) == pytest.approx(4, abs=1e-10)
+    assert s.B_face_right(7 + 2) == pytest.approx(7, abs=1e-10)
+    assert s.B_face_left(4 + 2) == pytest.approx(3, abs=1e-10)
+    assert s.B_face_left(7 + 2) == pytest.approx(6, abs=1e-10)
+    with pytest.raises(ValueError):   # DomainError in the reference (bottom_topography.jl:78-82)
+        O.OracleSim(dict(dim=1, nx=nx, gc=2, B=syn.cell_faces(nx, 2, 0.0, 10.0)))
+
+
+def test_bottom_topography_2d(O):
+    syn = cases.synthetic()
+    nx = ny = 2
+    xf = syn.cell_faces(nx, 2, 0.0, 12.0, interior=False)
+    yf = syn.cell_faces(ny, 2, 0.0, 20.0, interior=False)
+    B = xf[None, :] + yf[:, None]
+    s = O.OracleSim(dict(dim=2, nx=nx, ny=ny, gc=2, extent=[0, 12.0, 0, 20.0], B=B))
+    tol = 1e-10
+    assert s.B_cell(3, 3) == pytest.approx(8, abs=tol)
+    assert s.B_cell(3, 4) == pytest.approx(18, abs=tol)
+    assert s.B_cell(4, 3) == pytest.approx(14, abs=tol)
+    assert s.B_cell(4, 4) == pytest.approx(24, abs=tol)
+    assert s.B_face_left(3, 3, 0) == pytest.approx(5, abs=tol)
+    assert s.B_face_right(3, 3, 0) == pytest.approx(11, abs=tol)
+    assert s.B_face_left(3, 3, 1) == pytest.approx(3, abs=tol)
+    assert s.B_face_right(3, 3, 1) == pytest.approx(13, abs=tol)
+    assert s.B_face_left(4, 4, 0) == pytest.approx(21, abs=tol)
+    assert s.B_face_right(4, 4, 0) == pytest.approx(27, abs=tol)
+    assert s.B_face_left(4, 4, 1) == pytest.approx(19, abs=tol)
+    assert s.B_face_right(4, 4, 1) == pytest.approx(29, abs=tol)
+    assert s.B_face_right(3, 4, 0) == pytest.approx(s.B_face_left(4, 4, 0), abs=tol)
+    assert s.B_face_right(4, 3, 1) == pytest.approx(s.B_face_left(4, 4, 1), abs=tol)
+
+
+# ---- test_for_each_cell_2d.jl, test_for_each_inner_cell_2d.jl, test_for_each_ghost_cell_2d.jl ----
+def test_iteration_spaces_inner_2d(O):
+    nx, ny = 64, 32
+    s = O.OracleSim(dict(dim=2, nx=nx, ny=ny, gc=1))
+    cells = s.enumerate_cells()
+    assert len(cells) == (nx + 2) * (ny + 2)
+    for d in (0, 1):
+        tri = s.enumerate_inner_cells(d)
+        assert len(tri) == nx * ny
+        mid = {(a, b) for a, b in tri[:, 2:4]}
+        assert mid == {(x, y) for x in range(2, nx + 2) for y in range(2, ny + 2)}
+        if d == 0:
+            assert np.all(tri[:, 0] == tri[:, 2] - 1) and np.all(tri[:, 4] == tri[:, 2] + 1)
+            assert np.all(tri[:, 1] == tri[:, 3]) and np.all(tri[:, 5] == tri[:, 3])
+        else:
+            assert np.all(tri[:, 1] == tri[:, 3] - 1) and np.all(tri[:, 5] == tri[:, 3] + 1)
+            assert np.all(tri[:, 0] == tri[:, 2]) and np.all(tri[:, 4] == tri[:, 2])
+    # inner_cells(grid, XDIR, 0) == (nx + 2, ny)  (test_for_each_inner_cell_2d.jl:35-36)
+    assert len(s.enumerate_inner_cells(0, 0)) == (nx + 2) * ny
+    assert len(s.enumerate_inner_cells(1, 0)) == nx * (ny + 2)
+
+
+@pytest.mark.parametrize("gc", [1, 2])
+def test_iteration_spaces_ghost_2d(O, gc):
+    nx, ny = 11, 8
+    s = O.OracleSim(dict(dim=2, nx=nx, ny=ny, gc=gc))
+    gx = {tuple(r) for r in s.enumerate_ghost_cells(0)}
+    assert gx == {(i, j) for i in range(1, gc + 1) for j in range(gc + 1, ny + gc + 1)}
+    gy = {tuple(r) for r in s.enumerate_ghost_cells(1)}
+    assert gy == {(i, j) for j in range(1, gc + 1) for i in range(gc + 1, nx + gc + 1)}
+
+
+# ---- test_periodic_bc_2d.jl:26-74 -------------------------------------------------------------
+@pytest.mark.parametrize("gc", [1, 2])
+def test_periodic_bc_2d(O, gc):
+    nx, ny = 11, 8
+    s = O.OracleSim(dict(dim=2, nx=nx, ny=ny, gc=gc, bc="periodic", pure=True))
+    a = -42.0 * np.ones((3, ny + 2 * gc, nx + 2 * gc))
+    for j in range(gc + 1, ny + gc + 1):
+        for i in range(gc + 1, nx + gc + 1):
+            a[:, j - 1, i - 1] = j * nx + i
+    s.set_state_full(a)
+    s.update_bc()
+    out = s.get_state_full()[0].T   # -> out[i-1, j-1] like Julia output[i, j]
+    o = lambda i, j: out[i - 1, j - 1]
+    Nx, Ny = nx + 2 * gc, ny + 2 * gc
+    for j in range(gc + 1, ny + gc + 1):
+        for i in range(gc + 1, nx + gc + 1):
+            assert o(i, j) == j * nx + i
+    for i in range(gc + 1, nx + gc + 1):
+        for n in range(1, gc + 1):
+            assert o(i, n) == o(i, Ny - (gc - n + 1) - gc + 1)
+            assert o(i, Ny - (gc - n)) == o(i, gc + n)
+    for j in range(gc + 1, ny + gc + 1):
+        for n in range(1, gc + 1):
+            assert o(n, j) == o(Nx - (gc - n + 1) - gc + 1, j)
+            assert o(Nx - (gc - n), j) == o(gc + n, j)
+    # corners are never written (App. B)
+    assert o(1, 1) == -42 and o(Nx, Ny) == -42 and o(1, Ny) == -42 and o(Nx, 1) == -42
+
+
+# ---- test_update_bc.jl:51-117 (wall 1D and 2D) --------------------------------------------------
+def test_wall_bc_1d(O):
+    nx = 10
+    s = O.OracleSim(dict(dim=1, nx=nx, gc=2, bc="wall"))
+    u = np.stack([np.arange(1, nx + 5, dtype=float), 10.0 * np.arange(1, nx + 5)])
+    s.set_state_full(u)
+    s.update_bc()
+    v = s.get_state_full()
+    U = lambda i, k: v[k - 1, i - 1]
+    assert np.array_equal(v[:, 2:-2], u[:, 2:-2])
+    assert U(2, 1) == U(3, 1) and U(1, 1) == U(4, 1)
+    assert U(nx + 4, 1) == U(nx + 1, 1) and U(nx + 3, 1) == U(nx + 2, 1)
+    assert U(2, 2) == -U(3, 2) and U(1, 2) == -U(4, 2)
+    assert U(nx + 4, 2) == -U(nx + 1, 2) and U(nx + 3, 2) == -U(nx + 2, 2)
+
+
+def test_wall_bc_2d(O):
+    nx, ny = 10, 5
+    syn = cases.synthetic()
+    s = O.OracleSim(dict(dim=2, nx=nx, ny=ny, gc=2, bc="wall", pure=True))
+    x = syn.cell_centers(nx, 2, 0.0, 1.0, interior=False)
+    y = syn.cell_centers(ny, 2, 0.0, 1.0, interior=False)
+    X, Y = np.meshgrid(x, y)
+    u = np.stack([X, (X + Y) * 10, X * (Y - 5)])
+    s.set_state_full(u)
+    s.update_bc()
+    v = s.get_state_full()
+    f = lambda k: v[k - 1].T     # f(k)[i-1, j-1]
+    assert np.array_equal(v[:, 2:-2, 2:-2], u[:, 2:-2, 2:-2])
+    for k, sx, sy in ((1, 1, 1), (2, -1, 1), (3, 1, -1)):
+        a = f(k)
+        assert np.array_equal(a[1, 2:-2], sx * a[2, 2:-2])
+        assert np.array_equal(a[0, 2:-2], sx * a[3, 2:-2])
+        assert np.array_equal(a[nx + 3, 2:-2], sx * a[nx, 2:-2])
+        assert np.array_equal(a[nx + 2, 2:-2], sx * a[nx + 1, 2:-2])
+        assert np.array_equal(a[2:-2, 1], sy * a[2:-2, 2])
+        assert np.array_equal(a[2:-2, 0], sy * a[2:-2, 3])
+        assert np.array_equal(a[2:-2, ny + 3], sy * a[2:-2, ny])
+        assert np.array_equal(a[2:-2, ny + 2], sy * a[2:-2, ny + 1])
+
+
+# ---- test_rain.jl:55-66, 72-77 ; test_infiltration.jl:55-64, 70-76 ---------------------------------
+def test_rain_functions_and_run(O):
+    case, st = cases.rain_case(10, 0.01)
+    s = O.OracleSim(case)
+    assert s.rain_rate(12.6) == 0.01 / 3600.0
+    td = O.OracleSim(dict(case, rain=([0.015, 0.0003, 0.02], [0.0, 3600.0, 7200.0])))
+    assert td.rain_rate(10) == 0.015 / 3600.0
+    assert td.rain_rate(3610) == 0.0003 / 3600.0
+    assert td.rain_rate(7210) == 0.02 / 3600.0
+    assert td.rain_rate(1.0e6) == 0.02 / 3600.0
+    assert td.rain_rate(0.0) == 0.015 / 3600.0
+    s.set_state_interior(*st)
+    s.simulate_to_time(3 * 3600.0)
+    assert s.t == pytest.approx(3 * 3600.0, abs=1e-10)
+    w, hu, hv = s.get_state_interior()
+    assert np.all(hu == 0.0) and np.all(hv == 0.0)
+    assert w.max() == pytest.approx(3 * 0.01 + 1.0, abs=1e-12)
+    assert w.min() == pytest.approx(3 * 0.01 + 1.0, abs=1e-12)
+    # time dependent rain, 1 h (test_rain.jl:85-87)
+    td.set_state_interior(*st)
+    td.simulate_to_time(3600.0)
+    w = td.get_state_interior()[0]
+    assert w.max() == pytest.approx(0.015 + 1.0, abs=1e-12) and w.min() == pytest.approx(0.015 + 1.0, abs=1e-12)
+
+
+def test_infiltration_functions_and_run(O):
+    case, st = cases.infiltration_case()
+    s = O.OracleSim(case)
+    assert s.infiltration(0.0) == 1.977e-4
+    assert s.infiltration(1e6) == 3.272e-5
+    s.set_state_interior(*st)
+    s.simulate_to_time(1e6 + 1000.0)
+    w, hu, hv = s.get_state_interior()
+    assert np.all(hu == 0.0) and np.all(hv == 0.0)
+    assert w.max() == pytest.approx(1.0 - 3.272e-5 * 1000, abs=1e-10)
+    assert w.min() == pytest.approx(1.0 - 3.272e-5 * 1000, abs=1e-10)
+
+
+# ---- test_lake_at_rest_2d.jl:97-98 -----------------------------------------------------------------
+@pytest.mark.parametrize("which", ["step", "bumpy"])
+def test_lake_at_rest_2d(O, which):
+    case, st = cases.lake_at_rest_2d(which)
+    s = O.OracleSim(case)
+    s.set_state_interior(*st)
+    s.simulate_to_time(0.01)
+    w, hu, hv = s.get_state_interior()
+    assert np.max(np.abs(hu)) <= 1e-14
+    assert np.max(np.abs(hv)) <= 1e-14
+    assert abs(w[0, 0] - 0.7) <= 1e-14
+
+
+# ---- test_lake_at_rest.jl (1D, step + bumpy) ---------------------------------------------------------
+@pytest.mark.parametrize("which", ["step", "bumpy"])
+def test_lake_at_rest_1d(O, which):
+    syn = cases.synthetic()
+    nx = 64
+    if which == "step":
+        ext = [0.0, 10.0]
+        xf = syn.cell_faces(nx, 2, *ext, interior=False)
+        B = np.where(xf < 5.0, 0.45, 0.55)
+    else:
+        ext = [-2 * np.pi, 2 * np.pi]
+        xf = syn.cell_faces(nx, 2, *ext, interior=False)
+        B = np.cos(xf) - 0.5
+    s = O.OracleSim(dict(dim=1, nx=nx, gc=2, bc="wall", extent=ext, theta=2.0, cfl=0.2, stepper="fe",
+                         B=B, bottom_source=True))
+    s.set_state_interior(np.full(nx, 0.7), np.zeros(nx))
+    s.simulate_to_time(0.01)
+    w, hu = s.get_state_interior()
+    assert np.max(np.abs(hu)) <= 1e-14 and np.max(np.abs(w - 0.7)) <= 1e-14
+
+
+# ---- test_shallow_water_2d.jl:82, 105-117 ------------------------------------------------------------
+def test_gaussian_pure_2d_symmetry(O):
+    case, st = cases.gaussian_pure_2d()
+    nx, ny = case["nx"], case["ny"]
+    s = O.OracleSim(case)
+    s.set_state_interior(*st)
+    assert not np.any(np.isnan(s.get_state_full()))
+    T = 0.05
+    s.simulate_to_time(T)
+    assert s.t == T
+    w, hu, hv = [a.T for a in s.get_state_interior()]    # [x, y] indexing like the reference
+    tol = 1e-13
+    xl = nx // 3; xr = nx - xl + 1; yl = ny // 3; yu = ny - yl + 1
+    assert np.max(w[xl - 1, :] - w[xr - 1, :]) == pytest.approx(0, abs=tol)
+    assert np.max(w[:, yl - 1] - w[:, yu - 1]) == pytest.approx(0, abs=tol)
+    assert np.max(hu[xl - 1, :] + hu[xr - 1, :]) == pytest.approx(0, abs=tol)
+    assert np.max(hu[:, yl - 1] - hu[:, yu - 1]) == pytest.approx(0, abs=tol)
+    assert np.max(hv[xl - 1, :] - hv[xr - 1, :]) == pytest.approx(0, abs=tol)
+    assert np.max(hv[:, yl - 1] + hv[:, yu - 1]) == pytest.approx(0, abs=tol)
+    assert np.max(np.abs(hu)) > 1e-3      # the wave actually moved
+
+
+# ---- test_shallow_water_dry_states_2d.jl:87, 104-116 ---------------------------------------------------
+def test_dry_states_2d_symmetry(O):
+    case, st = cases.dry_states_2d()
+    n = case["nx"]
+    s = O.OracleSim(case)
+    s.set_state_interior(*st)
+    T = 0.05
+    s.simulate_to_time(T)
+    assert s.t == T
+    w, hu, hv = [a.T for a in s.get_state_interior()]
+    assert not np.any(np.isnan(w))
+    tol = 1e-12
+    xl = n // 3; xr = n - xl + 1
+    assert np.max(w[xl - 1, :] - w[xr - 1, :]) == pytest.approx(0, abs=tol)
+    assert np.max(w[:, xl - 1] - w[:, xr - 1]) == pytest.approx(0, abs=tol)
+    assert np.max(hu[xl - 1, :] + hu[xr - 1, :]) == pytest.approx(0, abs=tol)
+    assert np.max(hu[:, xl - 1] - hu[:, xr - 1]) == pytest.approx(0, abs=tol)
+    assert np.max(hv[xl - 1, :] - hv[xr - 1, :]) == pytest.approx(0, abs=tol)
+    assert np.max(hv[:, xl - 1] + hv[:, xr - 1]) == pytest.approx(0, abs=tol)
+    assert np.max(np.abs(hu)) > 1e-3
+
+
+# ---- test_swashes.jl:317-328 : x-run == y-run == 1D run, bitwise, equal dt ---------------------------
+@pytest.mark.parametrize("kind,T", [("411", 6.0), ("412", 4.0)])
+def test_swashes_xy1d_bitwise(O, kind, T):
+    nx = 512 if kind == "412" else 256    # 411 at 256 cells keeps the CPU suite short
+    sims = {}
+    for layout in ("x", "y", "1d"):
+        case, st = cases.swashes41x(kind, nx, layout)
+        s = O.OracleSim(case)
+        s.set_state_interior(*st)
+        s.simulate_to_time(T)
+        sims[layout] = s
+    wx, hux, hvx = sims["x"].get_state_interior()
+    wy, huy, hvy = sims["y"].get_state_interior()
+    w1, hu1 = sims["1d"].get_state_interior()
+    assert np.all(hvx == 0) and np.all(huy == 0)
+    h_x, hu_x = wx[1, :], hux[1, :]
+    h_y, hv_y = wy[:, 1], hvy[:, 1]
+    assert np.array_equal(h_y, h_x) and np.array_equal(hv_y, hu_x)
+    assert np.array_equal(w1, h_x) and np.array_equal(hu1, hu_x)
+    assert sims["x"].dt == sims["1d"].dt == sims["y"].dt
+    # accuracy vs the SWASHES analytic solution (the reference only plots this)
+    if kind == "412":
+        syn = cases.synthetic()
+        xc = syn.cell_centers(nx, 2, 0.0, 10.0)
+        h_ref, _ = cases.swashes412_analytic(xc, T)
+        assert np.mean(np.abs(h_x - h_ref)) < 2e-5      # L1 error, h ~ 5e-3
+
+
+# ---- test_swe1D_sim.jl:95-96,119-120 ; test_friction_1d.jl:90-91,114-115 ------------------------------
+@pytest.mark.parametrize("friction,stepper,tolB", [(None, "fe", 1e-6), ("bh2021", "rk2", 1e-2)])
+def test_swe_1d_pure_vs_practical(O, friction, stepper, tolB):
+    T = 0.05
+
+    def run(**kw):
+        case, st = cases.gaussian_1d(stepper=stepper, friction=friction, **kw)
+        s = O.OracleSim(case)
+        s.set_state_interior(*st)
+        s.simulate_to_time(T)
+        if friction is None:
+            assert s.t == T
+        return s.get_state_interior()
+
+    ref_h, ref_hu = run(pure=True)
+    h, hu = run(pure=False)
+    assert np.sum(np.abs(ref_h - h)) == pytest.approx(0, abs=1e-7)
+    assert np.sum(np.abs(ref_hu - hu)) == pytest.approx(0, abs=1e-7)
+    syn = cases.synthetic()
+    Bfield = np.ones(1024 + 5)
+    for B in (1.0, Bfield):
+        h, hu = run(pure=False, B=B, elevate=1.0, bottom_source=True)
+        assert np.sum(np.abs(ref_h - (h - 1))) == pytest.approx(0, abs=tolB)
+        assert np.sum(np.abs(ref_hu - hu)) == pytest.approx(0, abs=tolB)
+
+
+# ---- BASELINE config 1: examples/shallow_water_1d.jl:31-66,102 -----------------------------------------
+def test_config1_1d_example(O):
+    case, st = cases.gaussian_1d(pure=True, stepper="rk2", cfl=0.25, theta=1.05)
+    s = O.OracleSim(case)
+    s.set_state_interior(*st)
+    mass0 = st[0].sum()
+    n = s.simulate_to_time(0.05)
+    h, hu = s.get_state_interior()
+    assert s.t == 0.05 and n > 50
+    assert abs(h.sum() - mass0) < 1e-10 * mass0       # periodic: mass conserved
+    assert np.max(np.abs(h - h[::-1])) < 1e-12         # mirror symmetric IC stays symmetric
+    assert np.max(np.abs(hu + hu[::-1])) < 1e-12
+
+
+# ---- Float32 storage mode (Julia mixed-precision emulation) ---------------------------
+def test_float32_mode_close_to_float64(O):
+    out = {}
+    for dt in ("float64", "float32"):
+        case, st = cases.dry_states_2d(dtype=dt)
+        s = O.OracleSim(case)
+        s.set_state_interior(*st)
+        for _ in range(20):
+            s.step()
+        out[dt] = s.get_state_interior()
+    assert out["float32"][0].dtype == np.float32
+    for a, b in zip(out["float32"], out["float64"]):
+        assert cases.rel_linf(a, b) < 5e-5
