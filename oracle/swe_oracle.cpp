@@ -458,7 +458,15 @@ struct Oracle {
             dtl = jmin(cfl * ddt, max_dt);
         }
         const int64_t n = plane * nvar;
-        for (int64_t q = 0; q < n; ++q) out[q] = (S)(state[q] + dtl * out[q]);
+        if (substep == 0) {
+            // dt is the freshly computed Float64 local (rungekutta.jl:35,40)
+            for (int64_t q = 0; q < n; ++q) out[q] = (S)(state[q] + dtl * out[q]);
+        } else {
+            // dt is the argument = simulator.current_timestep[1], a realtype value: the whole
+            // expression stays in realtype (simulator.jl:151,155; rungekutta.jl:40)
+            const S dts = (S)dt_in;
+            for (int64_t q = 0; q < n; ++q) out[q] = (S)(state[q] + dts * out[q]);
+        }
         if (c.stepper == 1 && substep == 1) {
             const std::vector<S>& first = vol[cur[0]];
             for (int64_t q = 0; q < n; ++q) out[q] = (S)(0.5 * (first[q] + out[q]));

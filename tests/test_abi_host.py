@@ -1,0 +1,91 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/swe_b200.h declares, and the ctypes mirror of swe_b200_config has the C layout."""
+import ctypes as C
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "swe_b200.h"
+
+
+def test_library_loads_and_exports_all_declared_symbols(pkg):
+    lib = pkg.api._lib.lib()
+    declared = set(re.findall(r"\b(swe_b200_[a-z0-9_]+)\s*\(", HEADER.read_text()))
+    declared -= {"swe_b200_handle", "swe_b200_config", "swe_b200_timing"}
+    assert len(declared) >= 29
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/swe_b200.h but not exported"
+    assert declared == set(pkg.api._lib.SYMBOLS), "ctypes binding table and header disagree"
+
+
+def test_config_layout_matches_header(pkg, tmp_path):
+    src = tmp_path / "layout.c"
+    fields = ["abi_version", "gc", "fused", "device", "y_offset", "extent", "theta", "t0", "rain_rate", "k",
+              "rain_rates", "rain_times"]
+    body = "".join(f'printf("{f} %zu\\n", offsetof(swe_b200_config, {f}));\n' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "swe_b200.h"\nint main(void){\n'
+                   'printf("sizeof %zu\\n", sizeof(swe_b200_config));\n'
+                   'printf("timing %zu\\n", sizeof(swe_b200_timing));\n' + body + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    Cfg = pkg.api._lib.Config
+    assert int(out["sizeof"]) == C.sizeof(Cfg)
+    assert int(out["timing"]) == C.sizeof(pkg.api._lib.Timing)
+    for f in fields:
+        assert int(out[f]) == getattr(Cfg, f).offset, f
+
+
+def test_header_is_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "swe_b200.h"\nint main(void){return SWE_B200_ABI_VERSION == 1 ? 0 : 1;}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o",
+                    str(tmp_path / "t")], check=True)
+
+
+def test_host_side_validation_needs_no_gpu(pkg):
+    P = pkg
+    be = P.make_b200_backend(np.float32)
+    assert P.name(be) == "B200" and be.realtype is np.float32
+    grid = P.CartesianGrid(64, 32, gc=2, boundary=P.WallBC(), extent=[[0, 10.0], [0, 5.0]])
+    assert grid.totalcells == (68, 36) and P.compute_dx(grid) == 10.0 / 64 and P.compute_dy(grid) == 5.0 / 32
+    assert P.inner_cells(grid, P.XDIR) == (64, 32) and P.inner_cells(grid, P.XDIR, 0) == (68, 32)
+    assert P.inner_cells(grid, P.YDIR, 1) == (64, 34)
+    assert P.cell_faces(grid, interior=False).shape == (37, 69, 2)
+    with pytest.raises(P.DomainError):
+        P.BottomTopography2D(np.zeros((36, 68)), be, grid)
+    bt = P.BottomTopography2D(np.ones((37, 69)), be, grid)
+    eq = P.ShallowWaterEquations(bt, depth_cutoff=1e-3)
+    with pytest.raises(P.ArgumentError):
+        P.ConservedSystem(be, P.LinearReconstruction(), P.CentralUpwind(eq), eq, grid)
+    P.ConservedSystem(be, P.LinearReconstruction(), P.CentralUpwind(eq), eq, grid, [P.SourceTermBottom()])
+    with pytest.raises(P.DomainError):
+        P.TimeDependentRain([1.0, 2.0], [0.0])
+    with pytest.raises(P.B200Error):
+        P.FunctionalRain(lambda t, x, y: 0.0, grid)
+
+
+def test_no_cpu_fallback_in_product(pkg):
+    """the product package must not import or reference the oracle"""
+    pkg_dir = ROOT / "volumefluxes.jl_b200"
+    for p in list(pkg_dir.glob("*.py")) + list((pkg_dir / "csrc").glob("*")):
+        if p.suffix in (".py", ".cu", ".cuh", ".h"):
+            txt = p.read_text()
+            assert "liborc" not in txt and "swe_oracle" not in txt and "import oracle" not in txt, p
+
+
+def test_synthetic_terrain_is_deterministic():
+    syn = cases.synthetic()
+    a = syn.terrain_corners(64, 48, seed=1234)
+    b = syn.terrain_corners(64, 48, seed=1234)
+    assert a.shape == (53, 69) and a.dtype == np.float32 and np.array_equal(a, b)
+    assert np.ptp(a) > 10.0
+    c = syn.cell_average(a)
+    assert c.shape == (52, 68)

@@ -1,0 +1,386 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, plus the reference's own invariants re-run on the CUDA path.
+
+Tolerances (BASELINE.json north_star / SURVEY 8c):
+  strict policies  : bit-exact vs the oracle (every field, every step, dt sequence)
+  fast f64 (FMA)   : rel L-inf <= 1e-12 after N steps
+  fast f32         : rel L-inf <= 1e-5  after N steps, identical wet/dry masks
+"""
+import math
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+F64_TOL = 1e-12
+F32_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def P(pkg):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return pkg
+
+
+def both(P, oracle, case, state, strict, fused):
+    s = P.simulator_from_case(case, strict=strict, fused=fused)
+    o = oracle.OracleSim(case)
+    s.set_state_interior(*state)
+    o.set_state_interior(*state)
+    return s, o
+
+
+def interior(full, gc=2):
+    return full[:, gc:-gc, gc:-gc]
+
+
+def bc_written_equal(a, b, gc=2):
+    """compare interior + BC-written ghosts (corners are never written by any BC, App. B/C.2)"""
+    m = np.ones(a.shape[1:], dtype=bool)
+    m[:gc, :gc] = m[:gc, -gc:] = m[-gc:, :gc] = m[-gc:, -gc:] = False
+    return np.array_equal(a[:, m], b[:, m])
+
+
+SMALL_CASES = {
+    "dry_states_rk2": lambda dt: cases.dry_states_2d(dtype=dt, n=64),
+    "lake_step_fe": lambda dt: cases.lake_at_rest_2d("step", dtype=dt),
+    "terrain_wet": lambda dt: cases.terrain_case(n=96, dtype=dt, level=2.0, wavelength=64.0),
+    "terrain_rain_dry": lambda dt: cases.terrain_case(n=96, dtype=dt, wavelength=64.0, friction="fcg2016"),
+    "urban_norecon": lambda dt: cases.urban_case(n=96, dtype=dt, level=1.0, wavelength=64.0),
+    "lake_bh2021": lambda dt: cases.lake_case(n=100, ny=77, dtype=dt, level=0.0, wavelength=48.0),
+    "swashes_rk2": lambda dt: cases.swashes_dambreak_2d(n=64, dtype=dt),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. strict arithmetic: bit-exact against the oracle, operator by operator and step by step
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", ["terrain_wet", "urban_norecon", "dry_states_rk2"])
+def test_strict_operators_bit_exact(P, oracle, name, dtype):
+    case, state = SMALL_CASES[name](dtype)
+    s, o = both(P, oracle, case, state, strict=True, fused=False)
+    assert np.array_equal(s.get_state_full(), o.get_state_full())          # set_current_state! + update_bc!
+    for d in (0, 1):
+        s.reconstruct(d)
+        o.reconstruct(d)
+        ls, rs = s.get_faces()
+        lo, ro = o.get_faces()
+        assert np.array_equal(ls, lo) and np.array_equal(rs, ro), f"reconstruct dir {d}"
+    zero = np.zeros((3, o.Ny, o.Nx), dtype=dtype)
+    s.set_state_full(zero, 1)
+    o.set_state_full(zero, 1)
+    ms_s = s.add_time_derivative(0, 1, 0.0)
+    ms_o = o.add_time_derivative(0, 1, 0.0)
+    assert ms_s == ms_o
+    assert np.array_equal(s.get_state_full(1), o.get_state_full(1))
+    assert np.array_equal(s.get_wavespeeds(), o.get_wavespeeds())
+    if case.get("friction"):
+        s.implicit_substep(1, 0, 0.01)
+        o.implicit_friction(1, 0, 0.01)
+        assert np.array_equal(s.get_state_full(1), o.get_state_full(1))
+    s.post_proc_substep(1)
+    o.post_proc(1)
+    assert np.array_equal(s.get_state_full(1), o.get_state_full(1))
+    s.update_bc(1)
+    o.update_bc(1)
+    assert np.array_equal(s.get_state_full(1), o.get_state_full(1))
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", sorted(SMALL_CASES))
+def test_strict_steps_bit_exact(P, oracle, name, dtype, fused):
+    case, state = SMALL_CASES[name](dtype)
+    s, o = both(P, oracle, case, state, strict=True, fused=fused)
+    mts = case.get("maximum_timestep", math.inf)
+    for n in range(25):
+        s.step(mts)
+        o.step(mts)
+        assert s.dt == o.dt, f"dt differs at step {n}"
+        assert s.t == o.t
+    a, b = s.get_state_full(), o.get_state_full()
+    if fused:
+        assert bc_written_equal(a, b)      # fused kernels never touch the (unused) corner ghosts
+    else:
+        assert np.array_equal(a, b)
+    assert np.max(np.abs(interior(b)[1:])) > 0 or name in ("lake_step_fe",)   # something moved
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. fast arithmetic (the performance path): tolerance parity after N = 100 steps
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [("float64", F64_TOL), ("float32", F32_TOL)])
+@pytest.mark.parametrize("name", sorted(SMALL_CASES))
+def test_fast_fused_parity_100_steps(P, oracle, name, dtype, tol):
+    case, state = SMALL_CASES[name](dtype)
+    s, o = both(P, oracle, case, state, strict=False, fused=True)
+    mts = case.get("maximum_timestep", math.inf)
+    dts = []
+    for n in range(100):
+        s.step(mts)
+        o.step(mts)
+        dts.append((s.dt, o.dt))
+    a, b = interior(s.get_state_full()), interior(o.get_state_full())
+    for k, nm in enumerate(("w", "hu", "hv")):
+        assert cases.rel_linf(a[k], b[k]) <= tol, f"{nm}: {cases.rel_linf(a[k], b[k])}"
+    d = np.array(dts)
+    assert np.max(np.abs(d[:, 0] - d[:, 1]) / np.maximum(d[:, 1], 1e-300)) <= max(tol, 1e-6 if dtype == "float32" else tol)
+    if case.get("B") is not None and not np.isscalar(case.get("B")):
+        Bc = cases.synthetic().cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
+        wet_s = (a[0].astype(np.float64) - Bc) >= case["depth_cutoff"]
+        wet_o = (b[0].astype(np.float64) - Bc) >= case["depth_cutoff"]
+        assert np.array_equal(wet_s, wet_o), f"wet/dry masks differ in {np.sum(wet_s != wet_o)} cells"
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", F64_TOL), ("float32", F32_TOL)])
+def test_fast_unfused_matches_fused(P, dtype, tol):
+    case, state = SMALL_CASES["terrain_wet"](dtype)
+    a = P.simulator_from_case(case, fused=True)
+    b = P.simulator_from_case(case, fused=False)
+    for s in (a, b):
+        s.set_state_interior(*state)
+        s.run_steps(50, case.get("maximum_timestep"))
+    x, y = interior(a.get_state_full()), interior(b.get_state_full())
+    for k in range(3):
+        assert cases.rel_linf(x[k], y[k]) <= tol
+    assert a.t == pytest.approx(b.t, rel=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. the reference's own invariants, on the CUDA path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("strict,fused", [(False, True), (True, True), (False, False)])
+@pytest.mark.parametrize("which", ["step", "bumpy"])
+def test_lake_at_rest_2d(P, which, strict, fused):
+    """test_lake_at_rest_2d.jl:97-98"""
+    case, st = cases.lake_at_rest_2d(which)
+    s = P.simulator_from_case(case, strict=strict, fused=fused)
+    s.set_state_interior(*st)
+    P.simulate_to_time(s, 0.01)
+    w, hu, hv = s.get_state_interior()
+    assert s.t == 0.01
+    assert np.max(np.abs(hu)) <= 1e-14 and np.max(np.abs(hv)) <= 1e-14
+    assert abs(w[0, 0] - 0.7) <= 1e-14
+
+
+def test_lake_at_rest_float32(P):
+    case, st = cases.lake_at_rest_2d("bumpy", dtype="float32", stepper="rk2")
+    s = P.simulator_from_case(case)
+    s.set_state_interior(*st)
+    s.run_steps(50)
+    w, hu, hv = s.get_state_interior()
+    assert np.max(np.abs(hu)) <= 1e-6 and np.max(np.abs(hv)) <= 1e-6
+    assert np.max(np.abs(w - np.float32(0.7))) <= 1e-6
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_dry_states_symmetry_and_end_time(P, strict):
+    """test_shallow_water_dry_states_2d.jl:87, 104-116"""
+    case, st = cases.dry_states_2d()
+    n = case["nx"]
+    s = P.simulator_from_case(case, strict=strict)
+    s.set_state_interior(*st)
+    T = 0.05
+    nsteps = P.simulate_to_time(s, T)
+    assert s.t == T and nsteps > 10
+    w, hu, hv = [a.T for a in s.get_state_interior()]
+    assert not np.any(np.isnan(w))
+    tol = 1e-12
+    xl = n // 3; xr = n - xl + 1
+    assert abs(np.max(w[xl - 1, :] - w[xr - 1, :])) <= tol
+    assert abs(np.max(w[:, xl - 1] - w[:, xr - 1])) <= tol
+    assert abs(np.max(hu[xl - 1, :] + hu[xr - 1, :])) <= tol
+    assert abs(np.max(hu[:, xl - 1] - hu[:, xr - 1])) <= tol
+    assert abs(np.max(hv[xl - 1, :] - hv[xr - 1, :])) <= tol
+    assert abs(np.max(hv[:, xl - 1] + hv[:, xr - 1])) <= tol
+
+
+def test_gaussian_pure_unfused(P, oracle):
+    """test_shallow_water_2d.jl:82,105-117 (ShallowWaterEquationsPure -> per-operator kernels)"""
+    case, st = cases.gaussian_pure_2d()
+    s, o = both(P, oracle, case, st, strict=True, fused=True)   # fused flag is ignored for Pure
+    T = 0.05
+    ns = P.simulate_to_time(s, T)
+    no = o.simulate_to_time(T)
+    assert s.t == T and ns == no
+    assert np.array_equal(s.get_state_full(), o.get_state_full())
+    f = P.simulator_from_case(case)
+    f.set_state_interior(*st)
+    P.simulate_to_time(f, T)
+    assert cases.rel_linf(interior(f.get_state_full()), interior(o.get_state_full())) <= F64_TOL
+
+
+@pytest.mark.parametrize("strict,fused", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("kind,T", [("412", 4.0)])
+def test_swashes_x_equals_y_bitwise(P, oracle, kind, T, strict, fused):
+    """test_swashes.jl:317-328 on the CUDA path: the x-run and the y-run are bitwise mirror images,
+    with equal dt; in strict mode they also equal the oracle's 1D run bitwise."""
+    nx = 256
+    sims = {}
+    for layout in ("x", "y"):
+        case, st = cases.swashes41x(kind, nx, layout)
+        s = P.simulator_from_case(case, strict=strict, fused=fused)
+        s.set_state_interior(*st)
+        P.simulate_to_time(s, T)
+        sims[layout] = s
+    wx, hux, hvx = sims["x"].get_state_interior()
+    wy, huy, hvy = sims["y"].get_state_interior()
+    assert np.all(hvx == 0) and np.all(huy == 0)
+    assert np.array_equal(wy[:, 1], wx[1, :]) and np.array_equal(hvy[:, 1], hux[1, :])
+    assert sims["x"].dt == sims["y"].dt and sims["x"].t == T
+    case1, st1 = cases.swashes41x(kind, nx, "1d")
+    o = oracle.OracleSim(case1)
+    o.set_state_interior(*st1)
+    o.simulate_to_time(T)
+    h1, hu1 = o.get_state_interior()
+    if strict:
+        assert np.array_equal(h1, wx[1, :]) and np.array_equal(hu1, hux[1, :]) and o.dt == sims["x"].dt
+    else:
+        assert cases.rel_linf(wx[1, :], h1) <= 1e-9
+    xc = cases.synthetic().cell_centers(nx, 2, 0.0, 10.0)
+    h_ref, _ = cases.swashes412_analytic(xc, T)
+    assert np.mean(np.abs(wx[1, :] - h_ref)) < 4e-5
+
+
+def test_rain_and_infiltration(P):
+    """test_rain.jl:72-77, test_infiltration.jl:70-76"""
+    case, st = cases.rain_case(100, 0.01)
+    s = P.simulator_from_case(case)
+    s.set_state_interior(*st)
+    P.simulate_to_time(s, 3 * 3600.0)
+    assert s.t == pytest.approx(3 * 3600.0, abs=1e-10)
+    w, hu, hv = s.get_state_interior()
+    assert np.all(hu == 0.0) and np.all(hv == 0.0)
+    assert w.max() == pytest.approx(1.03, abs=1e-12) and w.min() == pytest.approx(1.03, abs=1e-12)
+    td = P.simulator_from_case(dict(case, rain=([0.015, 0.0003, 0.02], [0.0, 3600.0, 7200.0])))
+    td.set_state_interior(*st)
+    P.simulate_to_time(td, 3 * 3600.0)
+    w = td.get_state_interior()[0]
+    assert w.max() == pytest.approx(1.0353, abs=1e-4) and w.min() == pytest.approx(1.0353, abs=1e-4)
+    case, st = cases.infiltration_case()
+    s = P.simulator_from_case(case)
+    s.set_state_interior(*st)
+    P.simulate_to_time(s, 1e6 + 1000.0)
+    w, hu, hv = s.get_state_interior()
+    assert np.all(hu == 0.0) and np.all(hv == 0.0)
+    assert w.max() == pytest.approx(1.0 - 3.272e-5 * 1000, abs=1e-10)
+    assert w.min() == pytest.approx(1.0 - 3.272e-5 * 1000, abs=1e-10)
+
+
+def test_callback_loop_matches_device_loop(P):
+    case, st = cases.dry_states_2d(n=48)
+    a = P.simulator_from_case(case)
+    b = P.simulator_from_case(case)
+    for s in (a, b):
+        s.set_state_interior(*st)
+    seen = []
+    na = P.simulate_to_time(a, 0.02, callback=lambda t, sim: seen.append(t))
+    nb = P.simulate_to_time(b, 0.02)
+    assert na == nb == len(seen) and seen[-1] == 0.02
+    assert np.array_equal(a.get_state_full(), b.get_state_full())
+    c = P.simulator_from_case(case)
+    c.set_state_interior(*st)
+    nc = P.simulate_to_time(c, 0.02, match_endtime=False)
+    assert c.t >= 0.02 and nc <= nb
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. boundary conditions and iteration spaces (test_update_bc.jl, test_periodic_bc_2d.jl,
+#    test_for_each_*_2d.jl) through the device kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bc", ["periodic", "wall", "neumann"])
+@pytest.mark.parametrize("gc", [1, 2])
+def test_update_bc_matches_oracle(P, oracle, bc, gc):
+    nx, ny = 11, 8
+    case = dict(dim=2, nx=nx, ny=ny, gc=gc, bc=bc, pure=True, recon="none", stepper="fe")
+    s = P.simulator_from_case(case)
+    o = oracle.OracleSim(case)
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(3, ny + 2 * gc, nx + 2 * gc))
+    s.set_state_full(a)
+    o.set_state_full(a)
+    s.update_bc()
+    o.update_bc()
+    got = s.get_state_full()
+    assert np.array_equal(got, o.get_state_full())
+    assert np.array_equal(got[:, gc:-gc, gc:-gc], a[:, gc:-gc, gc:-gc])
+    assert np.array_equal(got[:, :gc, :gc], a[:, :gc, :gc])      # corners untouched
+
+
+def test_iteration_spaces(P, oracle):
+    nx, ny = 64, 32
+    grid = P.CartesianGrid(nx, ny)
+    be = P.make_b200_backend()
+    o = oracle.OracleSim(dict(dim=2, nx=nx, ny=ny, gc=1))
+    seen = []
+    P.for_each_cell(lambda I: seen.append(I), be, grid)
+    assert sorted(seen) == sorted(map(tuple, o.enumerate_cells()))
+    for d in (P.XDIR, P.YDIR):
+        tri = []
+        P.for_each_inner_cell(lambda l, m, r: tri.append(l + m + r), be, grid, d)
+        assert sorted(tri) == sorted(map(tuple, o.enumerate_inner_cells(d)))
+        tri0 = []
+        P.for_each_inner_cell(lambda l, m, r: tri0.append(l + m + r), be, grid, d, ghostcells=0)
+        assert sorted(tri0) == sorted(map(tuple, o.enumerate_inner_cells(d, 0)))
+    for gc in (1, 2):
+        grid = P.CartesianGrid(11, 8, gc=gc)
+        o = oracle.OracleSim(dict(dim=2, nx=11, ny=8, gc=gc))
+        for d in (P.XDIR, P.YDIR):
+            g = []
+            P.for_each_ghost_cell(lambda I: g.append(I), be, grid, d)
+            assert sorted(g) == sorted(map(tuple, o.enumerate_ghost_cells(d)))
+
+
+def test_error_behaviour(P):
+    be = P.make_b200_backend()
+    grid = P.CartesianGrid(8, 8, gc=2)
+    with pytest.raises(P.DomainError):
+        P.BottomTopography2D(np.zeros((8, 8)), be, grid)
+    bt = P.BottomTopography2D(np.ones((13, 13)), be, grid)
+    eq = P.ShallowWaterEquations(bt)
+    with pytest.raises(P.ArgumentError):      # equation.jl:83
+        P.ConservedSystem(be, P.LinearReconstruction(), P.CentralUpwind(eq), eq, grid)
+    with pytest.raises(P.ArgumentError):      # linearreconstruction.jl:59
+        g1 = P.CartesianGrid(8, 8, gc=1)
+        e1 = P.ShallowWaterEquations()
+        P.ConservedSystem(be, P.LinearReconstruction(), P.CentralUpwind(e1), e1, g1)
+    with pytest.raises(P.DomainError):
+        P.HortonInfiltration(P.CartesianGrid(2, 2), be, factor=np.ones((8, 8)))
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. size-independent properties at larger sizes (the oracle would take too long here)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_large_grid_properties(P, dtype):
+    n = 2048
+    case, st = cases.lake_case(n=n, dtype=dtype, level=0.0)
+    s = P.simulator_from_case(case)
+    s.set_state_interior(*st)
+    Bc = cases.synthetic().cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
+    vol0 = np.sum(st[0].astype(np.float64) - Bc)
+    s.run_steps(40)
+    w, hu, hv = s.get_state_interior()
+    assert not np.any(np.isnan(w)) and s.t > 0
+    h = w.astype(np.float64) - Bc
+    assert h.min() >= -1e-4                                   # depth positivity
+    vol1 = np.sum(h)
+    assert abs(vol1 - vol0) / vol0 < (1e-4 if dtype == "float32" else 1e-9)   # wall BC: volume conserved
+    assert np.max(np.abs(hu)) > 0
+    # ghost cells obey the wall BC exactly
+    full = s.get_state_full()
+    assert np.array_equal(full[0, 2:-2, 1], full[0, 2:-2, 2]) and np.array_equal(full[1, 2:-2, 1], -full[1, 2:-2, 2])
+    assert np.array_equal(full[2, 0, 2:-2], -full[2, 3, 2:-2])
+    # strict run of the same 40 steps stays within tolerance of the fast run
+    x = P.simulator_from_case(case, strict=True)
+    x.set_state_interior(*st)
+    x.run_steps(40)
+    tol = F32_TOL if dtype == "float32" else F64_TOL
+    for a, b in zip(s.get_state_interior(), x.get_state_interior()):
+        assert cases.rel_linf(a, b) <= tol

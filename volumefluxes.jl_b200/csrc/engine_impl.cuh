@@ -1,0 +1,530 @@
+// engine_impl.cuh -- EngineT<P>: owns the device memory of one Simulator (one y-strip on one GPU)
+// and launches the kernels.  Host orchestration mirrors simulator.jl:145-212 and system.jl:62-75.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <limits>
+#include <vector>
+
+#include "engine.h"
+#include "kernels_fused.cuh"
+
+namespace swe {
+
+#define SWE_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return SWE_B200_ECUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+template <class P>
+class EngineT : public Engine {
+    using S = typename P::S;
+    using C = typename P::C;
+
+public:
+    swe_b200_config cfg;
+    Par<C> par;
+    int Nx, Ny, gc;
+    long long plane;
+    cudaStream_t stream = nullptr;
+    S* vol[3] = {nullptr, nullptr, nullptr};
+    S *left = nullptr, *right = nullptr, *ws = nullptr;
+    S* B = nullptr;
+    double* factor = nullptr;
+    Ctl* ctl = nullptr;
+    Ctl* h_ctl = nullptr;   // pinned mirror
+    int cur[3] = {0, 1, 2};
+    int64_t launches = 0;
+    RainTable rt;
+    InfilPar ip;
+    bool fused_ok = false;
+    std::vector<cudaEvent_t> ev;   // per-stage-kernel timing events (timed runs only)
+    bool timing_on = false;
+
+    int init(const swe_b200_config& c) {
+        cfg = c;
+        gc = c.gc;
+        Nx = c.nx + 2 * gc;
+        Ny = c.ny + 2 * gc;
+        plane = (long long)Nx * Ny;
+        SWE_CUDA(cudaSetDevice(c.device));
+        SWE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        const int gny = c.global_ny > 0 ? c.global_ny : c.ny;
+        const double dx = (c.extent[1] - c.extent[0]) / c.nx;       // grid.jl:83-85
+        const double dy = (c.extent[3] - c.extent[2]) / gny;
+        par.Nx = Nx; par.Ny = Ny; par.gc = gc; par.plane = plane;
+        par.dx = (C)dx; par.dy = (C)dy; par.rdx = (C)(1 / dx); par.rdy = (C)(1 / dy);
+        par.theta = (C)c.theta; par.rho = (C)c.rho; par.g = (C)c.g;
+        par.half_rho_g = (C)(0.5 * c.rho * c.g);
+        par.cutoff = (C)c.depth_cutoff; par.kappa = (C)c.kappa;
+        par.two_kappa = (C)(2 * c.kappa); par.inv_two_kappa = (C)(1.0 / (2 * c.kappa));
+        par.half_kappa = (C)(c.kappa / 2.0);
+        par.Cz = (C)c.Cz; par.constB = (C)c.const_B;
+        par.bc = c.bc; par.eq_kind = c.eq_kind; par.friction = c.friction;
+        par.hasB = c.has_bathymetry; par.bottom_source = c.has_bottom_source;
+        // y boundaries of this strip are physical unless a neighbouring rank owns the rows beyond
+        // (periodic-y across ranks is an exchange between rank 0 and rank P-1)
+        const bool multi = c.nranks > 1;
+        par.ylo_phys = (!multi || (c.rank == 0 && c.bc != SWE_B200_BC_PERIODIC)) ? 1 : 0;
+        par.yhi_phys = (!multi || (c.rank == c.nranks - 1 && c.bc != SWE_B200_BC_PERIODIC)) ? 1 : 0;
+        for (int k = 0; k < 3; ++k) {
+            SWE_CUDA(cudaMalloc(&vol[k], sizeof(S) * plane * 3));
+            SWE_CUDA(cudaMemsetAsync(vol[k], 0, sizeof(S) * plane * 3, stream));
+        }
+        if (c.has_bathymetry) {
+            SWE_CUDA(cudaMalloc(&B, sizeof(S) * (size_t)(Nx + 1) * (Ny + 1)));
+            SWE_CUDA(cudaMemsetAsync(B, 0, sizeof(S) * (size_t)(Nx + 1) * (Ny + 1), stream));
+        }
+        if (c.infil_kind == SWE_B200_INFIL_HORTON) {
+            SWE_CUDA(cudaMalloc(&factor, sizeof(double) * plane));
+            std::vector<double> ones((size_t)plane, 1.0);   // HortonInfiltration default factor=1.0
+            SWE_CUDA(cudaMemcpyAsync(factor, ones.data(), sizeof(double) * plane, cudaMemcpyHostToDevice, stream));
+            SWE_CUDA(cudaStreamSynchronize(stream));
+        }
+        SWE_CUDA(cudaMalloc(&ctl, sizeof(Ctl)));
+        SWE_CUDA(cudaMallocHost(&h_ctl, sizeof(Ctl)));
+        std::memset(h_ctl, 0, sizeof(Ctl));
+        h_ctl->t = (double)(S)c.t0;
+        SWE_CUDA(cudaMemcpyAsync(ctl, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+        rt.kind = c.rain_kind; rt.n = c.n_rain; rt.rate = c.rain_rate;
+        for (int q = 0; q < 16; ++q) { rt.rates[q] = c.rain_rates[q]; rt.times[q] = c.rain_times[q]; }
+        ip.kind = c.infil_kind; ip.cst = c.infil_const; ip.f0 = c.f0; ip.fc = c.fc; ip.k = c.k;
+        // the fused stage kernels cover the practical 2D SWE with gc == 2 and periodic / wall BCs
+        fused_ok = c.fused && c.eq_kind == 0 && gc == 2 && c.bc != SWE_B200_BC_NEUMANN && c.nx >= 4 && c.ny >= 4;
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+
+    ~EngineT() override {
+        for (int k = 0; k < 3; ++k) cudaFree(vol[k]);
+        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl);
+        if (h_ctl) cudaFreeHost(h_ctl);
+        for (auto e : ev) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    int check() {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { err = std::string("kernel launch: ") + cudaGetErrorString(e); return SWE_B200_ECUDA; }
+        return SWE_B200_OK;
+    }
+    int ensure_face_buffers() {
+        if (left) return SWE_B200_OK;
+        SWE_CUDA(cudaMalloc(&left, sizeof(S) * plane * 3));
+        SWE_CUDA(cudaMalloc(&right, sizeof(S) * plane * 3));
+        SWE_CUDA(cudaMalloc(&ws, sizeof(S) * plane));
+        SWE_CUDA(cudaMemsetAsync(left, 0, sizeof(S) * plane * 3, stream));
+        SWE_CUDA(cudaMemsetAsync(right, 0, sizeof(S) * plane * 3, stream));
+        SWE_CUDA(cudaMemsetAsync(ws, 0, sizeof(S) * plane, stream));
+        return SWE_B200_OK;
+    }
+    Bathy<P> bathy() const { return Bathy<P>{B, Nx + 1, par.constB}; }
+    dim3 blk2() const { return dim3(32, 8); }
+    dim3 grd2() const { return dim3((Nx + 31) / 32, (Ny + 7) / 8); }
+    int grd1(long long n) const { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
+    bool bad_buffer(int b) { if (b < 0 || b > 2) { err = "buffer index out of range"; return true; } return false; }
+
+    int sync() override { SWE_CUDA(cudaStreamSynchronize(stream)); return SWE_B200_OK; }
+
+    int set_bathymetry(const void* Bh, int64_t n) override {
+        if (!cfg.has_bathymetry) { err = "config has ConstantBottomTopography"; return SWE_B200_EINVAL; }
+        if (n != (int64_t)(Nx + 1) * (Ny + 1)) {   // validate_bottom_topography, bottom_topography.jl:78-82
+            err = "Bottom topography should be of size (" + std::to_string(Nx + 1) + ", " + std::to_string(Ny + 1) + ")";
+            return SWE_B200_EDOMAIN;
+        }
+        SWE_CUDA(cudaMemcpyAsync(B, Bh, sizeof(S) * n, cudaMemcpyHostToDevice, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+    int set_infiltration_factor(const double* f, int64_t n) override {
+        if (cfg.infil_kind != SWE_B200_INFIL_HORTON) { err = "no HortonInfiltration configured"; return SWE_B200_EINVAL; }
+        if (n != plane) {   // validate_infiltration_factor, source_term_infiltration.jl:61-65
+            err = "Infiltration factor should be of size (" + std::to_string(Nx) + ", " + std::to_string(Ny) + ")";
+            return SWE_B200_EDOMAIN;
+        }
+        SWE_CUDA(cudaMemcpyAsync(factor, f, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+
+    // staging buffer reuse: left doubles as scratch for interior pack/unpack when present; else temp
+    int set_state_interior(const void* w, const void* hu, const void* hv) override {
+        const size_t n = (size_t)cfg.nx * cfg.ny;
+        S* tmp = nullptr;
+        SWE_CUDA(cudaMallocAsync(&tmp, sizeof(S) * n * 3, stream));
+        const void* src[3] = {w, hu, hv};
+        for (int k = 0; k < 3; ++k)
+            SWE_CUDA(cudaMemcpyAsync(tmp + k * n, src[k], sizeof(S) * n, cudaMemcpyHostToDevice, stream));
+        dim3 b(32, 8), g((cfg.nx + 31) / 32, (cfg.ny + 7) / 8);
+        k_pack_interior<S><<<g, b, 0, stream>>>(vol[cur[0]], tmp, cfg.nx, cfg.ny, Nx, gc, plane, 1);
+        ++launches;
+        SWE_CUDA(cudaFreeAsync(tmp, stream));
+        int rc = update_bc(0);
+        if (rc) return rc;
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return check();
+    }
+    int get_state_interior(void* w, void* hu, void* hv) override {
+        const size_t n = (size_t)cfg.nx * cfg.ny;
+        S* tmp = nullptr;
+        SWE_CUDA(cudaMallocAsync(&tmp, sizeof(S) * n * 3, stream));
+        dim3 b(32, 8), g((cfg.nx + 31) / 32, (cfg.ny + 7) / 8);
+        k_pack_interior<S><<<g, b, 0, stream>>>(vol[cur[0]], tmp, cfg.nx, cfg.ny, Nx, gc, plane, 0);
+        ++launches;
+        void* dst[3] = {w, hu, hv};
+        for (int k = 0; k < 3; ++k)
+            SWE_CUDA(cudaMemcpyAsync(dst[k], tmp + k * n, sizeof(S) * n, cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaFreeAsync(tmp, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return check();
+    }
+    int set_state_full(int b, const void* data) override {
+        if (bad_buffer(b)) return SWE_B200_EINVAL;
+        SWE_CUDA(cudaMemcpyAsync(vol[cur[b]], data, sizeof(S) * plane * 3, cudaMemcpyHostToDevice, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+    int get_state_full(int b, void* data) override {
+        if (bad_buffer(b)) return SWE_B200_EINVAL;
+        SWE_CUDA(cudaMemcpyAsync(data, vol[cur[b]], sizeof(S) * plane * 3, cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+    int pull_ctl() {
+        SWE_CUDA(cudaMemcpyAsync(h_ctl, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+    int set_time(double t, double dt) override {
+        int rc = pull_ctl();
+        if (rc) return rc;
+        h_ctl->t = (double)(S)t;
+        h_ctl->dt = dt;
+        h_ctl->dt_s = (double)(S)dt;
+        SWE_CUDA(cudaMemcpyAsync(ctl, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+    int get_time(double* t, double* dt) override {
+        int rc = pull_ctl();
+        if (rc) return rc;
+        *t = h_ctl->t;
+        *dt = h_ctl->dt_s;
+        return SWE_B200_OK;
+    }
+
+    // ---- fine-grained operators -------------------------------------------------------------------
+    void launch_bc(S* d) {
+        const int nxp = Ny - 2 * gc, nyp = Nx - 2 * gc;
+        k_bc<S><<<(nxp + 127) / 128, 128, 0, stream>>>(d, Nx, Ny, plane, gc, cfg.bc, 0, 1, 1);
+        k_bc<S><<<(nyp + 127) / 128, 128, 0, stream>>>(d, Nx, Ny, plane, gc, cfg.bc, 1, par.ylo_phys, par.yhi_phys);
+        launches += 2;
+    }
+    int update_bc(int b) override {
+        if (bad_buffer(b)) return SWE_B200_EINVAL;
+        launch_bc(vol[cur[b]]);
+        return check();
+    }
+    void launch_reconstruct(const S* in, int dir) {
+        const bool pure = cfg.eq_kind == 1;
+        if (cfg.recon == SWE_B200_RECON_LINEAR) {
+            if (pure) k_reconstruct<P, 1, true><<<grd2(), blk2(), 0, stream>>>(par, bathy(), in, left, right, dir);
+            else k_reconstruct<P, 1, false><<<grd2(), blk2(), 0, stream>>>(par, bathy(), in, left, right, dir);
+        } else {
+            if (pure) k_reconstruct<P, 0, true><<<grd2(), blk2(), 0, stream>>>(par, bathy(), in, left, right, dir);
+            else k_reconstruct<P, 0, false><<<grd2(), blk2(), 0, stream>>>(par, bathy(), in, left, right, dir);
+        }
+        ++launches;
+    }
+    int reconstruct(int dir, int in_buffer) override {
+        if (bad_buffer(in_buffer) || dir < 0 || dir > 1) return SWE_B200_EINVAL;
+        int rc = ensure_face_buffers();
+        if (rc) return rc;
+        launch_reconstruct(vol[cur[in_buffer]], dir);
+        return check();
+    }
+    int get_faces(void* l, void* r) override {
+        int rc = ensure_face_buffers();
+        if (rc) return rc;
+        SWE_CUDA(cudaMemcpyAsync(l, left, sizeof(S) * plane * 3, cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaMemcpyAsync(r, right, sizeof(S) * plane * 3, cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+    int get_wavespeeds(void* w) override {
+        int rc = ensure_face_buffers();
+        if (rc) return rc;
+        SWE_CUDA(cudaMemcpyAsync(w, ws, sizeof(S) * plane, cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+    // system.jl:62-75 on device buffers; the per-direction max lands in ctl->maxspeed_bits
+    void launch_time_derivative(S* out, const S* state) {
+        const bool pure = cfg.eq_kind == 1;
+        for (int dir = 0; dir < 2; ++dir) {
+            launch_reconstruct(state, dir);
+            if (dir == 0) {
+                if (pure) k_flux<P, true, 0><<<grd2(), blk2(), 0, stream>>>(par, out, left, right, ws, ctl);
+                else k_flux<P, false, 0><<<grd2(), blk2(), 0, stream>>>(par, out, left, right, ws, ctl);
+            } else {
+                if (pure) k_flux<P, true, 1><<<grd2(), blk2(), 0, stream>>>(par, out, left, right, ws, ctl);
+                else k_flux<P, false, 1><<<grd2(), blk2(), 0, stream>>>(par, out, left, right, ws, ctl);
+            }
+            ++launches;
+            if (cfg.has_bottom_source && !pure) {
+                k_bottom<P><<<grd2(), blk2(), 0, stream>>>(par, bathy(), out, left, right, dir);
+                ++launches;
+            }
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool do_infil = (pass == 0) == (cfg.infil_first != 0);
+            if (do_infil && cfg.infil_kind != SWE_B200_INFIL_NONE) {
+                k_point_source<P><<<grd1(plane), 256, 0, stream>>>(out, plane, ctl, 1, factor);
+                ++launches;
+            }
+            if (!do_infil && cfg.rain_kind != SWE_B200_RAIN_NONE) {
+                k_point_source<P><<<grd1(plane), 256, 0, stream>>>(out, plane, ctl, 0, nullptr);
+                ++launches;
+            }
+        }
+    }
+    int add_time_derivative(int in_buffer, int out_buffer, double t, double maxspeed[2]) override {
+        if (bad_buffer(in_buffer) || bad_buffer(out_buffer)) return SWE_B200_EINVAL;
+        int rc = ensure_face_buffers();
+        if (rc) return rc;
+        rc = pull_ctl();
+        if (rc) return rc;
+        const double t_saved = h_ctl->t;
+        h_ctl->t = (double)(S)t;
+        SWE_CUDA(cudaMemcpyAsync(ctl, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+        k_ctl_begin<<<1, 1, 0, stream>>>(ctl, rt, ip, 0.0, 0, 0, 0.0, 0.0);
+        ++launches;
+        launch_time_derivative(vol[cur[out_buffer]], vol[cur[in_buffer]]);
+        rc = pull_ctl();
+        if (rc) return rc;
+        maxspeed[0] = (double)Bits<S>::dec(h_ctl->maxspeed_bits[0]);
+        maxspeed[1] = (double)Bits<S>::dec(h_ctl->maxspeed_bits[1]);
+        h_ctl->t = t_saved;
+        SWE_CUDA(cudaMemcpyAsync(ctl, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return check();
+    }
+    void launch_friction(S* out, const S* prev, double dt_host, int use_host) {
+        if (cfg.friction == SWE_B200_FRICTION_NONE) return;
+        if (cfg.eq_kind == 1) k_friction<P, true><<<grd2(), blk2(), 0, stream>>>(par, bathy(), out, prev, ctl, dt_host, use_host);
+        else k_friction<P, false><<<grd2(), blk2(), 0, stream>>>(par, bathy(), out, prev, ctl, dt_host, use_host);
+        ++launches;
+    }
+    int implicit_substep(int out_buffer, int prev_buffer, double dt) override {
+        if (bad_buffer(out_buffer) || bad_buffer(prev_buffer)) return SWE_B200_EINVAL;
+        launch_friction(vol[cur[out_buffer]], vol[cur[prev_buffer]], dt, 1);
+        return check();
+    }
+    void launch_postproc(S* out) {
+        if (cfg.eq_kind != 0) return;   // post_proc_substep!(::System, ::Equation) = nothing for Pure
+        k_postproc<P><<<grd2(), blk2(), 0, stream>>>(par, bathy(), out);
+        ++launches;
+    }
+    int post_proc_substep(int b) override {
+        if (bad_buffer(b)) return SWE_B200_EINVAL;
+        launch_postproc(vol[cur[b]]);
+        return check();
+    }
+
+    // ---- one perform_step!, unfused: the reference's kernel sequence 1:1 (simulator.jl:145-177) ------
+    void step_unfused(int advance) {
+        const int nsub = cfg.stepper == SWE_B200_RK2 ? 2 : 1;
+        const long long n3 = plane * 3;
+        for (int s = 0; s < nsub; ++s) {
+            S* out = vol[cur[s + 1]];
+            const S* state = vol[cur[s]];
+            k_fill<S><<<grd1(n3), 256, 0, stream>>>(out, n3, (S)0);                    // rungekutta.jl:28-30
+            ++launches;
+            launch_time_derivative(out, state);
+            if (s == 0) { k_ctl_dt<S><<<1, 1, 0, stream>>>(ctl, (double)par_dx(), (double)par_dy(), (S)cfg.cfl); ++launches; }
+            k_axpy<P><<<grd1(n3), 256, 0, stream>>>(out, state, n3, ctl, s == 0 ? 0 : 1);   // :39-41
+            ++launches;
+            if (s == 1) { k_rkavg<P><<<grd1(n3), 256, 0, stream>>>(out, vol[cur[0]], n3); ++launches; }   // :44-49
+            launch_friction(out, state, 0.0, 0);
+            launch_postproc(out);
+            launch_bc(out);
+        }
+        std::swap(cur[0], cur[nsub]);
+        if (advance) { k_ctl_advance<S><<<1, 1, 0, stream>>>(ctl); ++launches; }
+    }
+    double par_dx() const { return (cfg.extent[1] - cfg.extent[0]) / cfg.nx; }
+    double par_dy() const { return (cfg.extent[3] - cfg.extent[2]) / (cfg.global_ny > 0 ? cfg.global_ny : cfg.ny); }
+
+    // ---- one perform_step!, fused --------------------------------------------------------------------
+    template <int STAGE>
+    void launch_stage(const S* U, const S* D, S* out) {
+        StageArgs<P> a;
+        a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl;
+        a.rain_kind = cfg.rain_kind; a.infil_kind = cfg.infil_kind; a.infil_first = cfg.infil_first;
+        a.rows = FUSED_ROWS;
+        const int nwarps = (cfg.nx + FUSED_VW - 1) / FUSED_VW;
+        dim3 g((nwarps + FUSED_WPB - 1) / FUSED_WPB, (cfg.ny + a.rows - 1) / a.rows);
+        dim3 b(FUSED_WPB * 32);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timing_on) {
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0, stream);
+        }
+        const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
+        if (B) {
+            if (lin) k_stage<P, 1, true, STAGE><<<g, b, 0, stream>>>(a);
+            else k_stage<P, 0, true, STAGE><<<g, b, 0, stream>>>(a);
+        } else {
+            if (lin) k_stage<P, 1, false, STAGE><<<g, b, 0, stream>>>(a);
+            else k_stage<P, 0, false, STAGE><<<g, b, 0, stream>>>(a);
+        }
+        ++launches;
+        if (timing_on) {
+            cudaEventRecord(e1, stream);
+            ev.push_back(e0); ev.push_back(e1);
+        }
+    }
+    void step_fused(int advance) {
+        S* U = vol[cur[0]];
+        S* D = vol[cur[1]];
+        launch_stage<1>(U, nullptr, D);
+        k_ctl_dt<S><<<1, 1, 0, stream>>>(ctl, par_dx(), par_dy(), (S)cfg.cfl);
+        ++launches;
+        S* next;
+        if (cfg.stepper == SWE_B200_RK2) {
+            next = vol[cur[2]];
+            launch_stage<2>(U, D, next);
+            std::swap(cur[0], cur[2]);
+        } else {
+            dim3 b(32, 8), g((cfg.nx + 31) / 32, (cfg.ny + 7) / 8);
+            if (B) k_update_fe<P, true><<<g, b, 0, stream>>>(par, bathy(), U, D, ctl);
+            else k_update_fe<P, false><<<g, b, 0, stream>>>(par, bathy(), U, D, ctl);
+            ++launches;
+            next = D;
+            std::swap(cur[0], cur[1]);
+        }
+        const int nthreads = (Ny - 2 * gc) + (Nx - 2 * gc);
+        k_bc_advance<S><<<(nthreads + 127) / 128, 128, 0, stream>>>(next, Nx, Ny, plane, gc, cfg.bc, par.ylo_phys,
+                                                                    par.yhi_phys, ctl, advance);
+        ++launches;
+    }
+    void one_step(double max_dt_host, int use_t_end, int match, double t_end, double max_timestep, int advance) {
+        k_ctl_begin<<<1, 1, 0, stream>>>(ctl, rt, ip, max_dt_host, use_t_end, match, t_end, max_timestep);
+        ++launches;
+        if (fused_ok) step_fused(advance);
+        else step_unfused(advance);
+    }
+    int prepare() {
+        if (!fused_ok) return ensure_face_buffers();
+        return SWE_B200_OK;
+    }
+
+    int step(double max_dt, int advance_time) override {
+        int rc = prepare();
+        if (rc) return rc;
+        one_step(max_dt, 0, 0, 0.0, 0.0, advance_time);
+        return check();
+    }
+    int run_steps(int64_t n, double maximum_timestep, swe_b200_timing* timing) override {
+        int rc = prepare();
+        if (rc) return rc;
+        const double inf = std::numeric_limits<double>::infinity();
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        const int64_t l0 = launches;
+        if (timing) {
+            SWE_CUDA(cudaEventCreate(&t0));
+            SWE_CUDA(cudaEventCreate(&t1));
+            timing_on = true;
+            SWE_CUDA(cudaStreamSynchronize(stream));
+            SWE_CUDA(cudaEventRecord(t0, stream));
+        }
+        for (int64_t s = 0; s < n; ++s) one_step(inf, 0, 0, 0.0, maximum_timestep, 1);
+        if (timing) {
+            SWE_CUDA(cudaEventRecord(t1, stream));
+            SWE_CUDA(cudaStreamSynchronize(stream));
+            timing_on = false;
+            float ms = 0;
+            SWE_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+            timing->total_ms = ms;
+            timing->launches = launches - l0;
+            double acc = 0;
+            for (size_t q = 0; q + 1 < ev.size(); q += 2) {
+                float m = 0;
+                cudaEventElapsedTime(&m, ev[q], ev[q + 1]);
+                acc += m;
+            }
+            timing->stage_kernel_ms = acc;
+            timing->stage_launches = (int64_t)(ev.size() / 2);
+            for (auto e : ev) cudaEventDestroy(e);
+            ev.clear();
+            cudaEventDestroy(t0);
+            cudaEventDestroy(t1);
+        }
+        return check();
+    }
+    // simulator.jl:179-212.  dt and t live on the device; the host reads t back every `batch` steps.
+    // Steps issued after t reached t_end are exact no-ops (dt = 0) and are not counted.
+    int simulate_to_time(double t_end, int match_endtime, double maximum_timestep, int64_t* nsteps) override {
+        int rc = prepare();
+        if (rc) return rc;
+        rc = pull_ctl();
+        if (rc) return rc;
+        const long long n0 = h_ctl->nsteps;
+        int batch = 1;
+        while (h_ctl->t < t_end) {
+            for (int s = 0; s < batch; ++s) one_step(0.0, 1, match_endtime, t_end, maximum_timestep, 1);
+            rc = check();
+            if (rc) return rc;
+            rc = pull_ctl();
+            if (rc) return rc;
+            if (std::isnan(h_ctl->t) || std::isnan(h_ctl->dt)) { err = "NaN time step"; break; }
+            if (batch < 32) batch *= 2;
+        }
+        if (nsteps) *nsteps = h_ctl->nsteps - n0;
+        return SWE_B200_OK;
+    }
+
+    int enumerate(int kind, int dir, int g, int64_t* out, int64_t* count) override {
+        long long na, nb;
+        int per;
+        if (kind == 0) { na = Nx; nb = Ny; per = 2; }
+        else if (kind == 1) { na = dir == 0 ? Nx - 2 * g : Nx - 2 * gc; nb = dir == 0 ? Ny - 2 * gc : Ny - 2 * g; per = 6; }
+        else { na = dir == 0 ? gc : Nx - 2 * gc; nb = dir == 0 ? Ny - 2 * gc : gc; per = 2; }
+        if (na < 0 || nb < 0) { err = "empty index space"; return SWE_B200_EINVAL; }
+        *count = na * nb;
+        if (!out || *count == 0) return SWE_B200_OK;
+        long long* d = nullptr;
+        SWE_CUDA(cudaMalloc(&d, sizeof(long long) * per * (*count)));
+        dim3 b(32, 8), gr((unsigned)((na + 31) / 32), (unsigned)((nb + 7) / 8));
+        k_enumerate<<<gr, b, 0, stream>>>(kind, dir, g, Nx, Ny, gc, d);
+        ++launches;
+        SWE_CUDA(cudaMemcpyAsync(out, d, sizeof(long long) * per * (*count), cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(d);
+        return check();
+    }
+
+    int get_ipc_handle(void*) override { err = "multi-GPU exchange not built yet"; return SWE_B200_EUNSUPPORTED; }
+    int open_peers(const void*) override { err = "multi-GPU exchange not built yet"; return SWE_B200_EUNSUPPORTED; }
+    int64_t launch_count() const override { return launches; }
+};
+
+template <class P>
+Engine* make_engine_t(const swe_b200_config& cfg, std::string& err) {
+    auto* e = new EngineT<P>();
+    int rc = e->init(cfg);
+    if (rc != SWE_B200_OK) {
+        err = e->err;
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+
+}  // namespace swe
