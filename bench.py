@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric : 2D SWE cell-updates/s  (interior cells x full RK2 steps / second; one step = perform_step!:
+         2 stages incl. friction, dry clean-up, ghost-cell BC and the CFL reduction)
+config : configs[4] -- 16384 x 16384 Float32 synthetic bathymetry, WallBC, minmod(1.2), bottom source,
+         bh2021 friction, RK2, cfl 0.25; at N > 1 the SAME grid is cut into y-strips (strong scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (one rank per GPU)
+  python bench.py --impl reference [...]                          the reference algorithm on the host CPU
+                                                                  (oracle restatement, all host threads)
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "2D SWE cell-updates/s"
+UNIT = "cell-updates/s"
+WORDS_STAGE1, WORDS_STAGE2 = 7, 10        # algorithmic words per cell: K1 reads U(3)+B(1) writes dU(3);
+                                          # K2 reads U(3)+dU(3)+B(1) writes U'(3)   
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_case(n: int, dtype: str, ny=None):
+    import cases
+    return cases.lake_case(n=n, ny=ny, dtype=dtype, level=0.0)
+
+
+def wet_fraction(case, state):
+    import cases
+    Bc = cases.synthetic().cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
+    return float(np.mean(state[0].astype(np.float64) - Bc >= case["depth_cutoff"]))
+
+
+def run_reference(args, rank):
+    """The reference's CPU algorithm (oracle restatement: the Julia package cannot run here, see
+    DESIGN.md) on the host cores, on a bounded crop of the same workload."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    threads = oracle.set_threads(os.cpu_count() or 1)
+    n = args.cpu_n
+    case, state = build_case(n, args.dtype)
+    o = oracle.OracleSim(case)
+    o.set_state_interior(*state)
+    for _ in range(args.warmup):
+        o.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.step()
+    dt = time.perf_counter() - t0
+    value = n * n * args.steps / dt
+    sample = f"{n}x{n} crop of the same synthetic terrain/IC generator, {args.steps} RK2 steps, {threads} OpenMP threads"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
+        "data": "synthetic", "config": workload_config(args, n, wet_fraction(case, state)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def workload_config(args, n, wet):
+    return {"workload": f"configs[4]: {n}x{n} {args.dtype} synthetic bathymetry (separable 5-octave hills, seed 1234), "
+                        f"lake at level 0 + Gaussian hump ({wet:.0%} of cells wet), WallBC, LinearReconstruction(1.2), "
+                        "CentralUpwind, SourceTermBottom, ImplicitFriction(bh2021), RungeKutta2, cfl 0.25, "
+                        "depth_cutoff = kappa = 1e-3",
+            "grid": [n, n], "arithmetic": "fast" if not args.strict else "strict",
+            "parallelism": f"y-strips x{args.gpus}" if args.gpus > 1 else "single GPU",
+            "l2": "working set (state 3 x 3 planes + B, > 10 GB at 16384^2) far exceeds the 126 MB L2; no flush needed"}
+
+
+def run_ours(args, rank, world):
+    import cases
+    import torch
+    P = cases.load_package()
+    if world > 1:
+        raise SystemExit("multi-GPU bench path not built yet")
+    n = args.n
+    t_setup = time.perf_counter()
+    case, state = build_case(n, args.dtype)
+    wet = wet_fraction(case, state)
+    # pinned host buffers for the end-to-end leg
+    pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in state]
+    host_in = [p.numpy() for p in pinned]
+    out_pinned = [torch.empty_like(p).pin_memory() for p in pinned]
+    sim = P.simulator_from_case(case, strict=args.strict, fused=not args.unfused, device=int(os.environ.get("LOCAL_RANK", 0)))
+    sim.set_state_interior(*host_in)
+    t_setup = time.perf_counter() - t_setup
+
+    # ---- device-resident leg: inputs already in HBM when the timed region starts -------------------
+    sim.run_steps(args.warmup)
+    sim.sync()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    sampler.start()
+    tm = sim.run_steps_timed(args.steps)
+    clocks = sampler.stop()
+    cells = n * n
+    sec = tm["total_ms"] * 1e-3
+    value = cells * args.steps / sec
+
+    # ---- end-to-end leg through the public API with HOST buffers -----------------------------------
+    # set_current_state!(host state) -> K x perform_step! -> collect(current_interior_state):
+    # the H2D upload of the inputs and the D2H read of the result are inside the timed region.
+    L = P.api._lib.lib()
+    import ctypes as C
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sim._check(L.swe_b200_set_state_interior(sim._h, *[ptr(p) for p in pinned]))
+    sim.run_steps(args.steps)
+    sim._check(L.swe_b200_get_state_interior(sim._h, *[ptr(p) for p in out_pinned]))
+    e2e_sec = time.perf_counter() - t0
+    itemsize = np.dtype(args.dtype).itemsize
+    io_bytes = 3 * cells * itemsize
+    assert np.isfinite(out_pinned[0].numpy()).all()
+
+    peak, peak_src = hbm_peak()
+    ns2 = max(tm["stage_launches"] // 2, 1)
+    k2_ms = tm["stage2_ms"] / ns2
+    k1_ms = tm["stage1_ms"] / ns2
+    achieved = WORDS_STAGE2 * itemsize * cells / (k2_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(f"k_stage2_{args.dtype}_{n}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_stage<..., STAGE=2> (K2)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": WORDS_STAGE2 * itemsize * cells,
+                "avg_launch_ms": k2_ms,
+                "k1": {"achieved": WORDS_STAGE1 * itemsize * cells / (k1_ms * 1e-3) / 1e9, "avg_launch_ms": k1_ms},
+                "step": {"achieved": (WORDS_STAGE1 + WORDS_STAGE2) * itemsize * cells * args.steps / sec / 1e9,
+                         "frac": (WORDS_STAGE1 + WORDS_STAGE2) * itemsize * cells * args.steps / sec / 1e9 / peak}}
+
+    # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----------------
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle
+        oracle.set_threads(1)
+        cn = args.cpu_n
+        ccase, cstate = build_case(cn, args.dtype)
+        o = oracle.OracleSim(ccase)
+        o.set_state_interior(*cstate)
+        o.step()
+        csteps = 3
+        t0 = time.perf_counter()
+        for _ in range(csteps):
+            o.step()
+        cdt = time.perf_counter() - t0
+        cpu = {"value": cn * cn * csteps / cdt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{cn}x{cn} crop of the same generator, {csteps} RK2 steps, scalar oracle restatement "
+                         "(the Julia reference cannot run here: no julia binary)"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tm["total_ms"] / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+        "config": workload_config(args, n, wet),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": cells * args.steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": io_bytes / args.steps,
+                "d2h_bytes_per_step": io_bytes / args.steps,
+                "pattern": f"set_current_state!(pinned host) + {args.steps} x perform_step! + collect(state) to pinned host",
+                "seconds": e2e_sec},
+        "gpu_launches": tm["launches"], "setup_seconds": t_setup,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--cpu-n", type=int, default=1024, dest="cpu_n")
+    ap.add_argument("--strict", action="store_true")
+    ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        if args.cpu_n == 1024:
+            args.cpu_n = 2048
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -158,6 +158,8 @@ typedef struct swe_b200_timing {
     double stage_kernel_ms;   /* sum over the fused stage kernels (K1+K2) or 0 if unfused */
     int64_t launches;         /* kernels launched by the library in the region            */
     int64_t stage_launches;   /* number of stage-kernel launches timed                    */
+    double stage1_ms;         /* sum over the stage-1 kernel launches (K1: U^n -> dU, CFL max) */
+    double stage2_ms;         /* sum over the stage-2 kernel launches (K2: U^n, dU -> U^{n+1}) */
 } swe_b200_timing;
 int swe_b200_run_steps_timed(swe_b200_handle* h, int64_t n, double maximum_timestep,
                              swe_b200_timing* out);

@@ -97,6 +97,8 @@ def lib():
         L.orc_enumerate_ghost_cells.argtypes = [vp, i32, vp]
         L.orc_enumerate_cells.restype = i64
         L.orc_enumerate_cells.argtypes = [vp, vp]
+        L.orc_set_threads.restype = i32
+        L.orc_set_threads.argtypes = [i32]
         _lib = L
     return _lib
 
@@ -296,6 +298,11 @@ class OracleSim:
         out = np.empty((n, 2), dtype=np.int64)
         lib().orc_enumerate_cells(self._h, _ptr(out))
         return out
+
+
+def set_threads(n: int) -> int:
+    """host threads used by the per-cell loops (0 = leave unchanged); returns the count in effect"""
+    return lib().orc_set_threads(int(n))
 
 
 def minmod(a, b, c):

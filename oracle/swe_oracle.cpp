@@ -23,6 +23,9 @@
 #include <limits>
 #include <type_traits>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 extern "C" {
 struct orc_config {
@@ -239,6 +242,7 @@ struct Oracle {
     void reconstruct(const std::vector<S>& in, int dir) {
         if (c.recon == 0) {
             // noreconstruction.jl:23-46 : ALL cells
+#pragma omp parallel for
             for (int64_t j = 0; j < Ny; ++j)
                 for (int64_t i = 0; i < Nx; ++i) {
                     for (int k = 0; k < nvar; ++k) {
@@ -247,6 +251,7 @@ struct Oracle {
                     }
                 }
             if (c.eq_kind == 0) {
+#pragma omp parallel for
                 for (int64_t j = 0; j < Ny; ++j)
                     for (int64_t i = 0; i < Nx; ++i) {
                         left[at(i, j, 0)] = (S)(in[at(i, j, 0)] - B_cell(i, j));
@@ -259,6 +264,7 @@ struct Oracle {
         int64_t i0, i1, j0, j1;
         inner_range(dir, 1, i0, i1, j0, j1);
         const int64_t di = dir == 0 ? 1 : 0, dj = dir == 0 ? 0 : 1;
+#pragma omp parallel for
         for (int64_t j = j0; j < j1; ++j)
             for (int64_t i = i0; i < i1; ++i) {
                 S ql[3], qc[3], qr[3];
@@ -294,6 +300,7 @@ struct Oracle {
         int64_t i0, i1, j0, j1;
         inner_range(dir, c.gc, i0, i1, j0, j1);
         const int64_t di = dir == 0 ? 1 : 0, dj = dir == 0 ? 0 : 1;
+#pragma omp parallel for
         for (int64_t j = j0; j < j1; ++j)
             for (int64_t i = i0; i < i1; ++i) {
                 S Rm[3], Lr[3], Rl[3], Lm[3];
@@ -310,6 +317,7 @@ struct Oracle {
                 ws[at(i, j, 0)] = (S)jmax(sr, sl);                                             // :28
             }
         S m = ws[0];
+#pragma omp parallel for reduction(max : m)
         for (int64_t q = 1; q < plane; ++q) m = (S)jmax(m, ws[q]);   // maximum(wavespeeds) :32
         return m;
     }
@@ -320,6 +328,7 @@ struct Oracle {
         const int mom = dir == 0 ? 1 : 2;
         int64_t i0, i1, j0, j1;
         inner_range(dir, c.gc, i0, i1, j0, j1);
+#pragma omp parallel for
         for (int64_t j = j0; j < j1; ++j)
             for (int64_t i = i0; i < i1; ++i) {
                 const double Br = B_face_right(i, j, dir);
@@ -343,6 +352,7 @@ struct Oracle {
         for (int pass = 0; pass < 2; ++pass) {
             const bool do_infil = (pass == 0) == (c.infil_first != 0);
             if (do_infil && c.infil_kind != 0) {
+#pragma omp parallel for
                 for (int64_t q = 0; q < plane; ++q) {
                     double f = c.infil_kind == 1 ? c.infil_const
                                                  : factor[q] * (c.fc + (c.f0 - c.fc) * std::exp(-c.k * tt));
@@ -351,6 +361,7 @@ struct Oracle {
             }
             if (!do_infil && c.rain_kind != 0) {
                 const double r = rain_rate(tt);
+#pragma omp parallel for
                 for (int64_t q = 0; q < plane; ++q) out[q] = (S)(out[q] + r);
             }
         }
@@ -377,6 +388,7 @@ struct Oracle {
     }
     void implicit_friction(std::vector<S>& out, const std::vector<S>& prev, S dts) {
         if (c.friction == 0) return;
+#pragma omp parallel for
         for (int64_t j = 0; j < Ny; ++j)
             for (int64_t i = 0; i < Nx; ++i) {
                 const double Bm = eqB_cell(i, j);
@@ -399,6 +411,7 @@ struct Oracle {
     // ---- timestepper/timestepper.jl:25-51 -------------------------------------------------
     void post_proc(std::vector<S>& out) {
         if (c.eq_kind != 0) return;
+#pragma omp parallel for
         for (int64_t j = 0; j < Ny; ++j)
             for (int64_t i = 0; i < Nx; ++i) {
                 const double b = B_cell(i, j);
@@ -446,7 +459,9 @@ struct Oracle {
     // ---- timestepper/rungekutta.jl:26-52, forwardeuler.jl:28-47 ----------------------------
     // returns the (unrounded, Float64) dt exactly like the Julia local variable
     double do_substep(std::vector<S>& out, int substep /*0-based*/, double dt_in, double max_dt, S tt) {
-        std::fill(out.begin(), out.end(), (S)0);
+        const int64_t n = plane * nvar;
+#pragma omp parallel for
+        for (int64_t q = 0; q < n; ++q) out[q] = (S)0;
         const std::vector<S>& state = vol[cur[substep]];
         S wavespeed[2];
         add_time_derivative(out, state, tt, wavespeed);
@@ -457,18 +472,20 @@ struct Oracle {
             if (c.dim == 2) ddt = jmin(ddt, dy / wavespeed[1]);
             dtl = jmin(cfl * ddt, max_dt);
         }
-        const int64_t n = plane * nvar;
         if (substep == 0) {
             // dt is the freshly computed Float64 local (rungekutta.jl:35,40)
+#pragma omp parallel for
             for (int64_t q = 0; q < n; ++q) out[q] = (S)(state[q] + dtl * out[q]);
         } else {
             // dt is the argument = simulator.current_timestep[1], a realtype value: the whole
             // expression stays in realtype (simulator.jl:151,155; rungekutta.jl:40)
             const S dts = (S)dt_in;
+#pragma omp parallel for
             for (int64_t q = 0; q < n; ++q) out[q] = (S)(state[q] + dts * out[q]);
         }
         if (c.stepper == 1 && substep == 1) {
             const std::vector<S>& first = vol[cur[0]];
+#pragma omp parallel for
             for (int64_t q = 0; q < n; ++q) out[q] = (S)(0.5 * (first[q] + out[q]));
         }
         return dtl;
@@ -639,6 +656,18 @@ int orc_implicit_friction(void* hp, int out_buffer, int prev_buffer, double dt) 
 }
 int orc_post_proc(void* hp, int which) {
     return dispatch(hp, [&](auto& o) { o.post_proc(o.vol[o.cur[which]]); return 0; });
+}
+
+// number of host threads for the per-cell loops (each iteration writes its own cell: results are
+// independent of the thread count).  Returns the count in effect.
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }
 
 // ---- scalar helpers pinned by the reference's unit tests ----------------------------------

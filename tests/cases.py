@@ -163,7 +163,7 @@ def gaussian_1d(pure=True, B=None, elevate=0.0, stepper="fe", cfl=0.2, friction=
 # BASELINE configs 3-5 on synthetic terrain
 # ------------------------------------------------------------------------------------------
 def terrain_case(n=4096, dtype="float32", bc="wall", friction="bsa2012", stepper="rk2", level=None,
-                 wavelength=512.0):
+                 wavelength=512.0, film=0.0):
     """config 3: terrain.jl-shaped, bottom source + Manning-type friction + rain + Horton."""
     syn = synthetic()
     npd = np.dtype(dtype)
@@ -173,7 +173,7 @@ def terrain_case(n=4096, dtype="float32", bc="wall", friction="bsa2012", stepper
                 B=B, bottom_source=True, rain=0.015, infiltration={}, infil_first=True,
                 friction=friction, maximum_timestep=1.0)
     if level is None:
-        w = syn.cell_average(B)[2:-2, 2:-2].astype(npd)          # IC w = B_cell (dry)
+        w = (syn.cell_average(B)[2:-2, 2:-2] + film).astype(npd)  # IC w = B_cell (dry) [+ a uniform film]
         state = (w, np.zeros_like(w), np.zeros_like(w))
     else:
         state = syn.lake_initial_state(B, 2, level, dtype=npd)
@@ -197,17 +197,46 @@ def urban_case(n=8192, dtype="float32", bc="wall", level=None, wavelength=512.0)
     return case, state
 
 
-def lake_case(n=16384, dtype="float32", level=0.0, wavelength=512.0, ny=None):
-    """config 5: WallBC, minmod 1.2, bottom source, bh2021 friction, RK2, cfl .25, partially wet."""
+def lake_case(n=16384, dtype="float32", level=0.0, wavelength=512.0, ny=None, cutoff=1e-3):
+    """config 5: WallBC, minmod 1.2, bottom source, bh2021 friction, RK2, cfl .25, partially wet
+    (~55 % of the cells).  depth_cutoff = kappa = 1e-3 (1 mm): at |w| ~ 10 m one Float32 ulp of the
+    stored free surface is 1e-6 m, so the reference's Float64-oriented default 1e-5 would sit only
+    10 ulps above the storage resolution."""
     syn = synthetic()
     npd = np.dtype(dtype)
     ny = n if ny is None else ny
     B = syn.terrain_corners(n, ny, 2, seed=1234, dtype=npd, wavelength=wavelength)
     case = dict(dim=2, dtype=dtype, nx=n, ny=ny, gc=2, bc="wall", extent=[0.0, float(n), 0.0, float(ny)],
-                depth_cutoff=1e-5, kappa=1e-5, theta=1.2, cfl=0.25, stepper="rk2", recon="linear",
+                depth_cutoff=cutoff, kappa=cutoff, theta=1.2, cfl=0.25, stepper="rk2", recon="linear",
                 B=B, bottom_source=True, friction="bh2021")
     state = syn.lake_initial_state(B, 2, level, dtype=npd)
     return case, state
+
+
+def perturb_ulp(state, dtype, seed=7):
+    """+-1 ulp (of the storage dtype) on a random half of the entries of each field: the smallest input
+    change the storage type can express.  Used to measure how ill-conditioned N steps of a case are."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for a in state:
+        a = np.ascontiguousarray(a, dtype=dtype).copy()
+        up = np.nextafter(a, np.asarray(np.inf, dtype=dtype))
+        dn = np.nextafter(a, np.asarray(-np.inf, dtype=dtype))
+        r = rng.integers(0, 4, size=a.shape)
+        a = np.where(r == 0, up, np.where(r == 1, dn, a))
+        out.append(a.astype(dtype))
+    # keep exact zeros exact (dry momentum): a subnormal momentum is not a meaningful perturbation
+    return tuple(np.where(np.asarray(s0) == 0, 0, a).astype(dtype) for a, s0 in zip(out, state))
+
+
+def field_errors(a, b):
+    """rel L-inf per field: w against max|w|, both momenta against max(|hu|,|hv|)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    dw = max(np.max(np.abs(b[0])), 1e-300)
+    dm = max(np.max(np.abs(b[1])), np.max(np.abs(b[2])), 1e-300)
+    return [float(np.max(np.abs(a[0] - b[0])) / dw), float(np.max(np.abs(a[1] - b[1])) / dm),
+            float(np.max(np.abs(a[2] - b[2])) / dm)]
 
 
 def rel_linf(a, b):

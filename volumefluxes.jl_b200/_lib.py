@@ -36,7 +36,8 @@ class Config(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("stage_kernel_ms", C.c_double),
-                ("launches", C.c_int64), ("stage_launches", C.c_int64)]
+                ("launches", C.c_int64), ("stage_launches", C.c_int64),
+                ("stage1_ms", C.c_double), ("stage2_ms", C.c_double)]
 
 
 # every symbol include/swe_b200.h declares: name -> (restype, argtypes)

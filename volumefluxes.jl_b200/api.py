@@ -479,7 +479,7 @@ class Simulator:
         tm = _lib.Timing()
         self._check(_lib.lib().swe_b200_run_steps_timed(self._h, int(n), float(maximum_timestep or 0.0), C.byref(tm)))
         return dict(total_ms=tm.total_ms, stage_kernel_ms=tm.stage_kernel_ms, launches=tm.launches,
-                    stage_launches=tm.stage_launches)
+                    stage_launches=tm.stage_launches, stage1_ms=tm.stage1_ms, stage2_ms=tm.stage2_ms)
 
     def sync(self):
         self._check(_lib.lib().swe_b200_sync(self._h))

@@ -44,6 +44,7 @@ public:
     InfilPar ip;
     bool fused_ok = false;
     std::vector<cudaEvent_t> ev;   // per-stage-kernel timing events (timed runs only)
+    std::vector<int> ev_stage;
     bool timing_on = false;
 
     int init(const swe_b200_config& c) {
@@ -207,6 +208,7 @@ public:
         h_ctl->t = (double)(S)t;
         h_ctl->dt = dt;
         h_ctl->dt_s = (double)(S)dt;
+        h_ctl->dt_report = h_ctl->dt_s;
         SWE_CUDA(cudaMemcpyAsync(ctl, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
         return SWE_B200_OK;
@@ -215,7 +217,7 @@ public:
         int rc = pull_ctl();
         if (rc) return rc;
         *t = h_ctl->t;
-        *dt = h_ctl->dt_s;
+        *dt = h_ctl->dt_report;
         return SWE_B200_OK;
     }
 
@@ -388,6 +390,7 @@ public:
         if (timing_on) {
             cudaEventRecord(e1, stream);
             ev.push_back(e0); ev.push_back(e1);
+            ev_stage.push_back(STAGE);
         }
     }
     void step_fused(int advance) {
@@ -453,16 +456,19 @@ public:
             SWE_CUDA(cudaEventElapsedTime(&ms, t0, t1));
             timing->total_ms = ms;
             timing->launches = launches - l0;
-            double acc = 0;
+            double acc[3] = {0, 0, 0};
             for (size_t q = 0; q + 1 < ev.size(); q += 2) {
                 float m = 0;
                 cudaEventElapsedTime(&m, ev[q], ev[q + 1]);
-                acc += m;
+                acc[ev_stage[q / 2]] += m;
             }
-            timing->stage_kernel_ms = acc;
+            timing->stage1_ms = acc[1];
+            timing->stage2_ms = acc[2];
+            timing->stage_kernel_ms = acc[1] + acc[2];
             timing->stage_launches = (int64_t)(ev.size() / 2);
             for (auto e : ev) cudaEventDestroy(e);
             ev.clear();
+            ev_stage.clear();
             cudaEventDestroy(t0);
             cudaEventDestroy(t1);
         }

@@ -16,6 +16,7 @@ struct Ctl {
     unsigned long long maxspeed_bits[2];  // bit pattern of the non-negative realtype max per direction
     double dt;            // unrounded Float64 dt of stage 1 (rungekutta.jl:35)
     double dt_s;          // dt rounded to realtype (simulator.jl:151 current_timestep)
+    double dt_report;     // current_timestep as the reference would report it: dt_s of the last real step
     double t;             // simulation time, realtype-rounded (simulator.jl:205)
     double t_end;         // simulate_to_time target
     double max_timestep;  // maximum_timestep (<=0: none)
@@ -133,9 +134,11 @@ __global__ void k_ctl_dt(Ctl* c, double dx, double dy, S cfl) {
     if (c->use_t_end) max_dt = c->match_endtime ? (c->t_end - c->t) : (double)INFINITY;
     if (c->max_timestep > 0) max_dt = fmin(max_dt, c->max_timestep);
     double dt = fmin(cfl * ddt, max_dt);
-    if (c->use_t_end && !(c->t < c->t_end)) dt = 0.0;
+    const bool past_end = c->use_t_end && !(c->t < c->t_end);
+    if (past_end) dt = 0.0;
     c->dt = dt;
     c->dt_s = (double)(S)dt;
+    if (!past_end) c->dt_report = c->dt_s;
 }
 
 // t += dt (simulator.jl:205), in realtype

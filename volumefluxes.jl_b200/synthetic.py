@@ -33,14 +33,18 @@ def cell_centers(n: int, gc: int, lo: float, hi: float, interior: bool = True) -
 
 
 def terrain_corners(nx: int, ny: int, gc: int = 2, extent=None, seed: int = 1234,
-                    amplitude: float = 40.0, wavelength: float = 512.0, slope: float = 0.0,
-                    depression: float = 15.0, dtype=np.float32, octaves: int = 5) -> np.ndarray:
+                    amplitude: float = None, wavelength: float = 512.0, slope: float = 0.0,
+                    depression: float = None, dtype=np.float32, octaves: int = 5) -> np.ndarray:
     """Smooth hills (sum of `octaves` separable sinusoid products with seeded phases) + a linear
     slope in x + one bay-like Gaussian depression.  Evaluated at the (nx+2gc+1) x (ny+2gc+1) cell
     corners (incl. ghost region), as BottomTopography2D expects (bottom_topography.jl:51-59).
     Every term is separable, so the field is one small GEMM: cheap even at 16389^2."""
     if extent is None:
         extent = [0.0, float(nx), 0.0, float(ny)]
+    if amplitude is None:
+        amplitude = 10.0 * wavelength / 512.0     # keeps hill slopes (~0.1 rms) independent of the wavelength
+    if depression is None:
+        depression = 0.375 * amplitude
     x = cell_faces(nx, gc, extent[0], extent[1], interior=False)
     y = cell_faces(ny, gc, extent[2], extent[3], interior=False)
     Lx, Ly = extent[1] - extent[0], extent[3] - extent[2]
@@ -88,7 +92,7 @@ def cell_average(Bc: np.ndarray) -> np.ndarray:
     return 0.25 * s.astype(np.float64)
 
 
-def lake_initial_state(Bc: np.ndarray, gc: int, level: float, hump: float = 2.0, dtype=np.float32):
+def lake_initial_state(Bc: np.ndarray, gc: int, level: float, hump: float = 0.5, dtype=np.float32):
     """w = max(B_cell, level) plus a Gaussian hump on the wet part; hu = hv = 0.  Interior only."""
     Bcell = cell_average(Bc)[gc:-gc, gc:-gc]
     ny, nx = Bcell.shape
