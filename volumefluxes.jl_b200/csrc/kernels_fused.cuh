@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
         // cell ja
         recon_cell<P, RECON, false>(p, q0, q1, q2, bface_y(1), bface_y(2), bcell_of(1), Ly0, Ry0);
         C s;
-        central_upwind<P, false, 1>(p, Rp, Ly0, Gl, s);
+        central_upwind<P, false, 1, true>(p, Rp, Ly0, Gl, s);
         if (out_lane) msy = (S)s;
         // rotate the state window: q0 = row ja, q1 = row ja+1
 #pragma unroll
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
 #pragma unroll
             for (int k = 0; k < 3; ++k) Ln[k] = shfl_dn1(Lx[k]);      // left face value of cell i+1
             C F[3], s;
-            central_upwind<P, false, 0>(p, Rx, Ln, F, s);             // face i+1/2
+            central_upwind<P, false, 0, true>(p, Rx, Ln, F, s);             // face i+1/2
             if (STAGE == 1 && xface_lane) msx = (S)mx((C)msx, s);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
             S Ly1[3], Ry1[3];
             recon_cell<P, RECON, false>(p, q0, q1, q2, bface_y(1), bface_y(2), bcell_of(1), Ly1, Ry1);   // cell j+1
             C G[3], s;
-            central_upwind<P, false, 1>(p, Ry0, Ly1, G, s);           // face j+1/2
+            central_upwind<P, false, 1, true>(p, Ry0, Ly1, G, s);           // face j+1/2
             if (STAGE == 1 && out_lane) msy = (S)mx((C)msy, s);
 #pragma unroll
             for (int k = 0; k < 3; ++k) dU[k] = (S)(dU[k] - p.rdy * (G[k] - Gl[k]));

@@ -146,46 +146,67 @@ __device__ __forceinline__ void flux_eig(const Par<typename P::C>& p, typename P
 
 // ---- Kurganov-Petrova central-upwind face flux, centralupwind.jl:32-45 (generic, used for the
 // Pure equations) and :48-77 (practical SWE with dry-state gating) ---------------------------------
-template <class P, bool PURE, int DIR>
+// Branch-free inside: both sides are evaluated and a dry side is masked to zero with selects (the
+// reference's `if h > cutoff` gating, same values).  VOTE = true (fused kernels, all 32 lanes
+// converged): a warp whose faces are all dry skips the evaluation altogether.
+template <class P, bool PURE, int DIR, bool VOTE = false>
 __device__ __forceinline__ void central_upwind(const Par<typename P::C>& p, const typename P::S fm[3],
                                                const typename P::S fp[3], typename P::C F[3],
                                                typename P::C& speed) {
     using S = typename P::S;
     using C = typename P::C;
-    C Fm[3] = {0, 0, 0}, Fp[3] = {0, 0, 0};
-    C em1 = 0, em2 = 0, ep1 = 0, ep2 = 0;
-    if (PURE || fm[0] > p.cutoff) flux_eig<P, PURE, DIR>(p, fm[0], fm[1], fm[2], Fm, em1, em2);
-    if (PURE || fp[0] > p.cutoff) flux_eig<P, PURE, DIR>(p, fp[0], fp[1], fp[2], Fp, ep1, ep2);
+    const bool wm = PURE || fm[0] > p.cutoff;
+    const bool wp = PURE || fp[0] > p.cutoff;
+    if (!PURE) {
+        bool any = wm || wp;
+        if (VOTE) any = __any_sync(0xffffffffu, any);
+        if (!any) {
+            F[0] = F[1] = F[2] = 0;
+            speed = 0;
+            return;
+        }
+    }
+    C Fm[3], Fp[3], em1, em2, ep1, ep2;
+    flux_eig<P, PURE, DIR>(p, fm[0], fm[1], fm[2], Fm, em1, em2);
+    flux_eig<P, PURE, DIR>(p, fp[0], fp[1], fp[2], Fp, ep1, ep2);
+    if (!PURE) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            Fm[k] = wm ? Fm[k] : (C)0;
+            Fp[k] = wp ? Fp[k] : (C)0;
+        }
+        em1 = wm ? em1 : (C)0;
+        em2 = wm ? em2 : (C)0;
+        ep1 = wp ? ep1 : (C)0;
+        ep2 = wp ? ep2 : (C)0;
+    }
     const C ap = mx(mx(ep1, em1), (C)0);
     const C am = mn(mn(ep2, em2), (C)0);
     const C d = ap - am;
-    if (!PURE && ab(d) < p.kappa) {
-        F[0] = F[1] = F[2] = 0;
-        speed = 0;
-        return;
-    }
+    const bool ok = PURE || !(ab(d) < p.kappa);          // centralupwind.jl:67-69
     if constexpr (P::strict) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             S jump = fp[k] - fm[k];
-            F[k] = (ap * Fm[k] - am * Fp[k]) / d + ((ap * am) / d) * jump;
+            const C val = (ap * Fm[k] - am * Fp[k]) / d + ((ap * am) / d) * jump;
+            F[k] = ok ? val : (C)0;
         }
     } else {
-        const C r = (C)1 / d;
+        const C r = ok ? (C)1 / d : (C)0;
         const C c2 = ap * am * r;
 #pragma unroll
         for (int k = 0; k < 3; ++k) F[k] = (ap * Fm[k] - am * Fp[k]) * r + c2 * (C)(fp[k] - fm[k]);
     }
-    if (!PURE && fm[0] < p.cutoff && fp[0] < p.cutoff) speed = 0;
-    else speed = mx(ab(ap), ab(am));
+    const bool both_dry = !PURE && fm[0] < p.cutoff && fp[0] < p.cutoff;   // :73-75
+    speed = (!ok || both_dry) ? (C)0 : mx(ab(ap), ab(am));
 }
 
 // ---- minmod-limited slope, linearreconstruction.jl:28-43 -------------------------------------------
+// minmod(a,b,c) = min if all > 0, max if all < 0, else 0 -- evaluated without branches as
+// max(0, min3) + min(0, max3): exactly one of the two terms is non-zero, so the value is identical.
 template <class C>
 __device__ __forceinline__ C minmod3(C a, C b, C c) {
-    if (a > 0 && b > 0 && c > 0) return mn(mn(a, b), c);
-    if (a < 0 && b < 0 && c < 0) return mx(mx(a, b), c);
-    return (C)0;
+    return mx((C)0, mn(mn(a, b), c)) + mn((C)0, mx(mx(a, b), c));
 }
 template <class P>
 __device__ __forceinline__ typename P::C minmod_slope(typename P::S l, typename P::S c, typename P::S r,
@@ -219,8 +240,10 @@ __device__ __forceinline__ void recon_cell(const Par<typename P::C>& p, const ty
         const C half = (C)0.5;
         if constexpr (!PURE) {
             const S w = c[0];
-            if (w - half * s[0] < Bl) s[0] = (C)2.0 * (w - Bl);
-            else if (w + half * s[0] < Br) s[0] = (C)2.0 * (Br - w);
+            const bool c1 = w - half * s[0] < Bl;          // negative depth on the left face  (:81-84)
+            const bool c2 = w + half * s[0] < Br;          // negative depth on the right face (:86-89)
+            const C s1 = (C)2.0 * (w - Bl), s2 = (C)2.0 * (Br - w);
+            s[0] = c1 ? s1 : (c2 ? s2 : s[0]);
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
