@@ -110,32 +110,49 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
     };
     auto bface_y = [&](int r) -> C { return HASB ? (C)0.5 * (ca[r] + cb[r]) : p.constB; };
 
-    // ---- row loader: U^n (stage 1) or the rebuilt U^1 (stage 2) at (column ic, row j) ----
-    auto load_row = [&](int j, C bc_actual, S q[3], S un[3]) {
+    // ---- row loader, split in two so that the loads of row j+3 are in flight during row j's math:
+    //      issue_row : raw global loads of U^n (and dU in stage 2) at (column ic, row j)
+    //      finish_row: stage 1: q = U^n ; stage 2: q = the rebuilt U^1 = BC(postproc(friction(U^n + dt*dU)))
+    auto issue_row = [&](int j, S u[3], S d[3]) {
         if (STAGE == 1) {
             const S* s = a.U + (size_t)j * Nx + ic;
-            q[0] = s[0];
-            q[1] = s[plane];
-            q[2] = s[2 * plane];
+            u[0] = s[0];
+            u[1] = s[plane];
+            u[2] = s[2 * plane];
         } else {
             bool yflip;
             const int ys = bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
             const size_t off = (size_t)ys * Nx + xs;
-            S d[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                un[k] = a.U[off + k * plane];
+                u[k] = a.U[off + k * plane];
                 d[k] = a.D[off + k * plane];
             }
+        }
+    };
+    auto finish_row = [&](int j, const S u[3], const S d[3], C bc_actual, S q[3], S un[3]) {
+        if (STAGE == 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) q[k] = u[k];
+        } else {
+            bool yflip;
+            const int ys = bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) un[k] = u[k];
             C Bm = bc_actual;
             if (HASB && (xs != ic || ys != j)) {
                 const S* r0 = a.B + (size_t)ys * Bp + xs;
                 Bm = (C)0.25 * (r0[0] + r0[1] + r0[Bp] + r0[Bp + 1]);
             }
-            substep_tail<P>(p, un, d, dt, dt_s, Bm, q);
+            substep_tail<P>(p, u, d, dt, dt_s, Bm, q);
             if (xflip) q[1] = -q[1];
             if (yflip) q[2] = -q[2];
         }
+    };
+    auto load_row = [&](int j, C bc_actual, S q[3], S un[3]) {
+        S u[3], d[3] = {0, 0, 0};
+        issue_row(j, u, d);
+        finish_row(j, u, d, bc_actual, q, un);
     };
 
     // ---- prologue: rows ja-2 .. ja+1, corner rows ja-1 .. ja+1(+1) ----
@@ -173,10 +190,17 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
     }
 
     // ---- march ----
+    S ru[3], rd[3] = {0, 0, 0}, pa = 0, pb = 0;          // prefetched raw row j+2 and corner row j+3
+    issue_row(min(ja + 2, Ny - 1), ru, rd);
+    load_corners(min(ja + 3, Ny), pa, pb);
+#pragma unroll 2
     for (int j = ja; j < jb; ++j) {
         // window: qm = row j-1, q0 = row j, q1 = row j+1 ; corners ca[0..2] = rows j..j+2
-        load_corners(j + 3, ca[3], cb[3]);                 // needed for bcell(j+2) (stage 2 / RECON 0)
-        load_row(j + 2, bcell_of(2), q2, un2);
+        ca[3] = pa;                                        // corner row j+3: bcell(j+2) (stage 2 / RECON 0)
+        cb[3] = pb;
+        finish_row(j + 2, ru, rd, bcell_of(2), q2, un2);
+        issue_row(min(j + 3, Ny - 1), ru, rd);             // in flight during this row's arithmetic
+        load_corners(min(j + 4, Ny), pa, pb);
 
         S dU[3];
         // ================= x direction (row j) =================
