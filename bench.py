@@ -149,29 +149,67 @@ def run_ours(args, rank, world):
     import cases
     import torch
     P = cases.load_package()
-    if world > 1:
-        raise SystemExit("multi-GPU bench path not built yet")
     n = args.n
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.perf_counter()
-    case, state = build_case(n, args.dtype)
+    if world > 1:
+        case, state, y0 = cases.lake_strip_case(n, rank, world, dtype=args.dtype)
+        rows = case["ny"]
+    else:
+        case, state = build_case(n, args.dtype)
+        y0, rows = 0, n
     wet = wet_fraction(case, state)
     # pinned host buffers for the end-to-end leg
     pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in state]
     host_in = [p.numpy() for p in pinned]
     out_pinned = [torch.empty_like(p).pin_memory() for p in pinned]
-    sim = P.simulator_from_case(case, strict=args.strict, fused=not args.unfused, device=int(os.environ.get("LOCAL_RANK", 0)))
-    sim.set_state_interior(*host_in)
+    if world > 1:
+        strip = P.multigpu.StripSimulator(case, host_in, rank, world, n, y0, P.multigpu.torch_all_gather,
+                                          device=local, strict=args.strict)
+        sim = strip.sim
+        w = torch.tensor([wet * rows], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w)
+        wet = float(w.item()) / n
+    else:
+        sim = P.simulator_from_case(case, strict=args.strict, fused=not args.unfused, device=local)
+        sim.set_state_interior(*host_in)
     t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        sim.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
 
     # ---- device-resident leg: inputs already in HBM when the timed region starts -------------------
     sim.run_steps(args.warmup)
-    sim.sync()
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    barrier()
+    sampler = ClockSampler(local)
     sampler.start()
-    tm = sim.run_steps_timed(args.steps)
+    tm = sim.run_steps_timed(args.steps)       # CUDA events on the library's stream around the K steps
+    barrier()
     clocks = sampler.stop()
     cells = n * n
-    sec = tm["total_ms"] * 1e-3
+    sec = max_over_ranks(tm["total_ms"]) * 1e-3
     value = cells * args.steps / sec
 
     # ---- end-to-end leg through the public API with HOST buffers -----------------------------------
@@ -180,21 +218,28 @@ def run_ours(args, rank, world):
     L = P.api._lib.lib()
     import ctypes as C
     ptr = lambda t: C.c_void_p(t.data_ptr())
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     sim._check(L.swe_b200_set_state_interior(sim._h, *[ptr(p) for p in pinned]))
     sim.run_steps(args.steps)
     sim._check(L.swe_b200_get_state_interior(sim._h, *[ptr(p) for p in out_pinned]))
-    e2e_sec = time.perf_counter() - t0
+    e2e_sec = max_over_ranks(time.perf_counter() - t0)
     itemsize = np.dtype(args.dtype).itemsize
     io_bytes = 3 * cells * itemsize
     assert np.isfinite(out_pinned[0].numpy()).all()
+    launches = sum_over_ranks(float(tm["launches"]))
+    cells_local = n * rows
+    if rank != 0:
+        barrier()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     peak, peak_src = hbm_peak()
     ns2 = max(tm["stage_launches"] // 2, 1)
     k2_ms = tm["stage2_ms"] / ns2
     k1_ms = tm["stage1_ms"] / ns2
-    achieved = WORDS_STAGE2 * itemsize * cells / (k2_ms * 1e-3) / 1e9
+    achieved = WORDS_STAGE2 * itemsize * cells_local / (k2_ms * 1e-3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
@@ -204,15 +249,15 @@ def run_ours(args, rank, world):
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_stage<..., STAGE=2> (K2)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": WORDS_STAGE2 * itemsize * cells,
-                "avg_launch_ms": k2_ms,
-                "k1": {"achieved": WORDS_STAGE1 * itemsize * cells / (k1_ms * 1e-3) / 1e9, "avg_launch_ms": k1_ms},
-                "step": {"achieved": (WORDS_STAGE1 + WORDS_STAGE2) * itemsize * cells * args.steps / sec / 1e9,
-                         "frac": (WORDS_STAGE1 + WORDS_STAGE2) * itemsize * cells * args.steps / sec / 1e9 / peak}}
+                "algorithmic_bytes_per_launch": WORDS_STAGE2 * itemsize * cells_local,
+                "avg_launch_ms": k2_ms, "per": "GPU (rank 0's strip)" if world > 1 else "GPU",
+                "k1": {"achieved": WORDS_STAGE1 * itemsize * cells_local / (k1_ms * 1e-3) / 1e9, "avg_launch_ms": k1_ms},
+                "step": {"achieved": (WORDS_STAGE1 + WORDS_STAGE2) * itemsize * cells_local * args.steps / sec / 1e9,
+                         "frac": (WORDS_STAGE1 + WORDS_STAGE2) * itemsize * cells_local * args.steps / sec / 1e9 / peak}}
 
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         from oracle import oracle
         oracle.set_threads(1)
         cn = args.cpu_n
@@ -239,9 +284,12 @@ def run_ours(args, rank, world):
                 "d2h_bytes_per_step": io_bytes / args.steps,
                 "pattern": f"set_current_state!(pinned host) + {args.steps} x perform_step! + collect(state) to pinned host",
                 "seconds": e2e_sec},
-        "gpu_launches": tm["launches"], "setup_seconds": t_setup,
+        "gpu_launches": int(launches), "setup_seconds": t_setup,
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    barrier()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

@@ -145,10 +145,14 @@ int swe_b200_enumerate_ghost_cells(swe_b200_handle* h, int dir, int64_t* out /*[
                                    int64_t* count);
 
 /* ---- multi-GPU (y-strips; one process per GPU) -------------------------------------------- */
-/* 64-byte CUDA IPC handle of this rank's exchange window (halo rows + dt mailbox). */
-int swe_b200_get_ipc_handle(swe_b200_handle* h, void* handle64);
-/* Map the windows of the y-neighbours (NULL = physical boundary).  all_handles: nranks x 64 B. */
-int swe_b200_open_peers(swe_b200_handle* h, const void* all_handles64);
+/* 128-byte descriptor (CUDA IPC handle + strip layout) of this rank's exchange window: the three
+ * state volumes and the mailbox for halo stamps / CFL maxima.  Ranks exchange the descriptors with any
+ * host-side all-gather (torch.distributed in the Python host, MPI in a Julia host). */
+#define SWE_B200_IPC_BYTES 128
+int swe_b200_get_ipc_handle(swe_b200_handle* h, void* blob128);
+/* Map every rank's window (all_blobs: nranks x 128 B, ordered by rank).  Afterwards set_state_interior,
+ * step, run_steps and simulate_to_time are COLLECTIVE: every rank must issue the same sequence. */
+int swe_b200_open_peers(swe_b200_handle* h, const void* all_blobs128);
 
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* Runs n steps like run_steps and returns the device time (CUDA events on the handle's stream)

@@ -239,6 +239,22 @@ def field_errors(a, b):
             float(np.max(np.abs(a[2] - b[2])) / dm)]
 
 
+def lake_strip_case(n, rank, nranks, dtype="float32", level=0.0, wavelength=512.0, cutoff=1e-3):
+    """config 5 generated directly as the y-strip of `rank` (no rank ever materialises the global arrays).
+    Returns (strip case dict, strip state, y_offset)."""
+    from_pkg = load_package()
+    syn = from_pkg.synthetic
+    offsets, sizes = from_pkg.multigpu.partition_rows(n, nranks)
+    y0, nr = offsets[rank], sizes[rank]
+    npd = np.dtype(dtype)
+    B = syn.terrain_corners(n, n, 2, seed=1234, dtype=npd, wavelength=wavelength, row_range=(y0, y0 + nr + 5))
+    case = dict(dim=2, dtype=dtype, nx=n, ny=nr, gc=2, bc="wall", extent=[0.0, float(n), 0.0, float(n)],
+                depth_cutoff=cutoff, kappa=cutoff, theta=1.2, cfl=0.25, stepper="rk2", recon="linear",
+                B=B, bottom_source=True, friction="bh2021")
+    state = syn.lake_initial_state(B, 2, level, dtype=npd, y_offset=y0, ny_global=n)
+    return case, state, y0
+
+
 def rel_linf(a, b):
     """SURVEY 8c parity protocol: max|a-b| / max|b| per field."""
     den = np.max(np.abs(b))

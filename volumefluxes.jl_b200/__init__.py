@@ -9,3 +9,4 @@ goes through the CUDA library and fails loudly if it is missing.
 from . import synthetic  # noqa: F401
 from .api import *  # noqa: F401,F403
 from . import api  # noqa: F401
+from . import multigpu  # noqa: F401

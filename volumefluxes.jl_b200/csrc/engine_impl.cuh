@@ -8,6 +8,9 @@
 #include <vector>
 
 #include "engine.h"
+#include <unistd.h>
+
+#include "kernels_exchange.cuh"
 #include "kernels_fused.cuh"
 
 namespace swe {
@@ -20,6 +23,17 @@ namespace swe {
             return SWE_B200_ECUDA;                                                              \
         }                                                                                       \
     } while (0)
+
+// What one rank publishes about its exchange window (swe_b200_get_ipc_handle): 128 bytes.
+struct IpcBlob {
+    cudaIpcMemHandle_t handle;   // 64 B
+    long long pid;               // same-process peers use the raw pointer instead of the IPC handle
+    void* base;
+    long long Ny, plane, vol_bytes, mbox_offset;
+    int device, rank;
+    char pad[128 - 64 - 8 - 8 - 32 - 8];
+};
+static_assert(sizeof(IpcBlob) == 128, "IpcBlob must be 128 bytes");
 
 template <class P>
 class EngineT : public Engine {
@@ -43,6 +57,20 @@ public:
     RainTable rt;
     InfilPar ip;
     bool fused_ok = false;
+    // ---- multi-GPU exchange window: the three volumes + the mailbox live in ONE allocation ----
+    char* slab = nullptr;
+    size_t vol_bytes = 0, mbox_offset = 0, slab_bytes = 0;
+    Mailbox* mbox = nullptr;
+    unsigned int* ticket = nullptr;
+    bool peers_open = false;
+    char* peer_base[MAX_RANKS] = {};
+    long long peer_Ny[MAX_RANKS] = {}, peer_plane[MAX_RANKS] = {}, peer_vol_bytes[MAX_RANKS] = {};
+    Mailbox* peer_mbox[MAX_RANKS] = {};
+    bool peer_ipc[MAX_RANKS] = {};
+    int lo_rank = -1, hi_rank = -1;
+    unsigned long long xseq = 0;        // halo exchange stamp counter (identical on all ranks)
+    unsigned long long sseq = 0;        // step sequence for the CFL all-gather
+    unsigned long long pending_U = 0;   // stamp of the last U exchange the next K1 must wait for
     std::vector<cudaEvent_t> ev;   // per-stage-kernel timing events (timed runs only)
     std::vector<int> ev_stage;
     bool timing_on = false;
@@ -73,9 +101,20 @@ public:
         const bool multi = c.nranks > 1;
         par.ylo_phys = (!multi || (c.rank == 0 && c.bc != SWE_B200_BC_PERIODIC)) ? 1 : 0;
         par.yhi_phys = (!multi || (c.rank == c.nranks - 1 && c.bc != SWE_B200_BC_PERIODIC)) ? 1 : 0;
-        for (int k = 0; k < 3; ++k) {
-            SWE_CUDA(cudaMalloc(&vol[k], sizeof(S) * plane * 3));
-            SWE_CUDA(cudaMemsetAsync(vol[k], 0, sizeof(S) * plane * 3, stream));
+        vol_bytes = (sizeof(S) * plane * 3 + 255) / 256 * 256;
+        mbox_offset = 3 * vol_bytes;
+        slab_bytes = mbox_offset + 1024;
+        SWE_CUDA(cudaMalloc(&slab, slab_bytes));
+        SWE_CUDA(cudaMemsetAsync(slab, 0, slab_bytes, stream));
+        for (int k = 0; k < 3; ++k) vol[k] = (S*)(slab + k * vol_bytes);
+        mbox = (Mailbox*)(slab + mbox_offset);
+        ticket = (unsigned int*)(slab + mbox_offset + 768);
+        static_assert(sizeof(Mailbox) <= 768, "mailbox too large");
+        if (multi) {
+            if (c.nranks > MAX_RANKS) { err = "at most 8 ranks"; return SWE_B200_EUNSUPPORTED; }
+            const bool per = c.bc == SWE_B200_BC_PERIODIC;
+            lo_rank = c.rank > 0 ? c.rank - 1 : (per ? c.nranks - 1 : -1);
+            hi_rank = c.rank < c.nranks - 1 ? c.rank + 1 : (per ? 0 : -1);
         }
         if (c.has_bathymetry) {
             SWE_CUDA(cudaMalloc(&B, sizeof(S) * (size_t)(Nx + 1) * (Ny + 1)));
@@ -97,12 +136,18 @@ public:
         ip.kind = c.infil_kind; ip.cst = c.infil_const; ip.f0 = c.f0; ip.fc = c.fc; ip.k = c.k;
         // the fused stage kernels cover the practical 2D SWE with gc == 2 and periodic / wall BCs
         fused_ok = c.fused && c.eq_kind == 0 && gc == 2 && c.bc != SWE_B200_BC_NEUMANN && c.nx >= 4 && c.ny >= 4;
+        if (multi && !fused_ok) {
+            err = "y-strip decomposition needs the fused path (ShallowWaterEquations, gc == 2, periodic/wall BC)";
+            return SWE_B200_EUNSUPPORTED;
+        }
         SWE_CUDA(cudaStreamSynchronize(stream));
         return SWE_B200_OK;
     }
 
     ~EngineT() override {
-        for (int k = 0; k < 3; ++k) cudaFree(vol[k]);
+        for (int r = 0; r < MAX_RANKS; ++r)
+            if (peer_ipc[r] && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
+        cudaFree(slab);
         cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (auto e : ev) cudaEventDestroy(e);
@@ -131,7 +176,10 @@ public:
     int grd1(long long n) const { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
     bool bad_buffer(int b) { if (b < 0 || b > 2) { err = "buffer index out of range"; return true; } return false; }
 
-    int sync() override { SWE_CUDA(cudaStreamSynchronize(stream)); return SWE_B200_OK; }
+    int sync() override {
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return check_timeout();
+    }
 
     int set_bathymetry(const void* Bh, int64_t n) override {
         if (!cfg.has_bathymetry) { err = "config has ConstantBottomTopography"; return SWE_B200_EINVAL; }
@@ -168,6 +216,7 @@ public:
         SWE_CUDA(cudaFreeAsync(tmp, stream));
         int rc = update_bc(0);
         if (rc) return rc;
+        if (peers_open) push_halo(vol[cur[0]], cur[0], 2, false);   // collective: every rank sets its state
         SWE_CUDA(cudaStreamSynchronize(stream));
         return check();
     }
@@ -393,15 +442,62 @@ public:
             ev_stage.push_back(STAGE);
         }
     }
+    // ---- multi-GPU: peer pushes of halo rows / CFL maxima (kernels_exchange.cuh) -------------------------
+    // kind 0: dU rows (stamp slots 0/1), kind 2: U rows (slots 2/3); rows_only=false also publishes the speeds
+    void push_halo(const S* src, int vol_index, int kind, bool with_speed, bool rows = true) {
+        PushArgs<S> a{};
+        a.src = src;
+        a.src_plane = plane;
+        a.Nx = Nx; a.Ny = Ny; a.gc = gc;
+        a.rows = rows ? gc : 0;
+        if (rows) a.stamp = ++xseq;
+        if (lo_rank >= 0) {
+            a.dst_lo = (S*)(peer_base[lo_rank] + (size_t)vol_index * peer_vol_bytes[lo_rank]);
+            a.lo_plane = peer_plane[lo_rank];
+            a.lo_Ny = (int)peer_Ny[lo_rank];
+            a.flag_lo = &peer_mbox[lo_rank]->halo_stamp[kind + 1];   // I am the lower rank's UPPER neighbour
+        }
+        if (hi_rank >= 0) {
+            a.dst_hi = (S*)(peer_base[hi_rank] + (size_t)vol_index * peer_vol_bytes[hi_rank]);
+            a.hi_plane = peer_plane[hi_rank];
+            a.flag_hi = &peer_mbox[hi_rank]->halo_stamp[kind + 0];
+        }
+        a.with_speed = with_speed ? 1 : 0;
+        a.nranks = cfg.nranks; a.rank = cfg.rank; a.seq = sseq; a.ctl = ctl;
+        for (int r = 0; r < cfg.nranks; ++r) a.mbox[r] = peer_mbox[r];
+        a.ticket = ticket;
+        const long long total = (long long)a.rows * Nx * 6;
+        const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 64));
+        k_halo_push<S><<<blocks, 256, 0, stream>>>(a);
+        ++launches;
+        if (rows && kind == 2) pending_U = a.stamp;
+    }
+
     void step_fused(int advance) {
+        const bool multi = peers_open;
         S* U = vol[cur[0]];
         S* D = vol[cur[1]];
+        if (multi && pending_U) {   // the neighbours' U rows of the previous exchange must have landed
+            k_wait_halo<<<1, 1, 0, stream>>>(mbox, 2, lo_rank >= 0, hi_rank >= 0, pending_U);
+            ++launches;
+            pending_U = 0;
+        }
         launch_stage<1>(U, nullptr, D);
-        k_ctl_dt<S><<<1, 1, 0, stream>>>(ctl, par_dx(), par_dy(), (S)cfg.cfl);
+        const bool rk2 = cfg.stepper == SWE_B200_RK2;
+        if (multi) {
+            ++sseq;
+            push_halo(D, cur[1], 0, true, rk2);     // dU rows (RK2 only) + this rank's CFL maxima
+            k_ctl_dt_multi<S><<<1, 1, 0, stream>>>(ctl, mbox, par_dx(), par_dy(), (S)cfg.cfl, cfg.nranks, sseq,
+                                                   lo_rank >= 0, hi_rank >= 0, rk2 ? xseq : 0ull);
+        } else {
+            k_ctl_dt<S><<<1, 1, 0, stream>>>(ctl, par_dx(), par_dy(), (S)cfg.cfl);
+        }
         ++launches;
         S* next;
-        if (cfg.stepper == SWE_B200_RK2) {
+        int next_index;
+        if (rk2) {
             next = vol[cur[2]];
+            next_index = cur[2];
             launch_stage<2>(U, D, next);
             std::swap(cur[0], cur[2]);
         } else {
@@ -410,12 +506,14 @@ public:
             else k_update_fe<P, false><<<g, b, 0, stream>>>(par, bathy(), U, D, ctl);
             ++launches;
             next = D;
+            next_index = cur[1];
             std::swap(cur[0], cur[1]);
         }
         const int nthreads = (Ny - 2 * gc) + (Nx - 2 * gc);
         k_bc_advance<S><<<(nthreads + 127) / 128, 128, 0, stream>>>(next, Nx, Ny, plane, gc, cfg.bc, par.ylo_phys,
                                                                     par.yhi_phys, ctl, advance);
         ++launches;
+        if (multi) push_halo(next, next_index, 2, false);
     }
     void one_step(double max_dt_host, int use_t_end, int match, double t_end, double max_timestep, int advance) {
         k_ctl_begin<<<1, 1, 0, stream>>>(ctl, rt, ip, max_dt_host, use_t_end, match, t_end, max_timestep);
@@ -516,8 +614,59 @@ public:
         return check();
     }
 
-    int get_ipc_handle(void*) override { err = "multi-GPU exchange not built yet"; return SWE_B200_EUNSUPPORTED; }
-    int open_peers(const void*) override { err = "multi-GPU exchange not built yet"; return SWE_B200_EUNSUPPORTED; }
+    int get_ipc_handle(void* out128) override {
+        IpcBlob b;
+        std::memset(&b, 0, sizeof(b));
+        SWE_CUDA(cudaIpcGetMemHandle(&b.handle, slab));
+        b.pid = (long long)getpid();
+        b.base = slab;
+        b.Ny = Ny; b.plane = plane; b.vol_bytes = (long long)vol_bytes; b.mbox_offset = (long long)mbox_offset;
+        b.device = cfg.device; b.rank = cfg.rank;
+        std::memcpy(out128, &b, sizeof(b));
+        return SWE_B200_OK;
+    }
+    int open_peers(const void* all128) override {
+        if (cfg.nranks <= 1) { err = "open_peers on a single-rank handle"; return SWE_B200_EINVAL; }
+        const IpcBlob* blobs = (const IpcBlob*)all128;
+        SWE_CUDA(cudaSetDevice(cfg.device));
+        for (int r = 0; r < cfg.nranks; ++r) {
+            const IpcBlob& b = blobs[r];
+            if (b.rank != r) { err = "peer handles must be ordered by rank"; return SWE_B200_EINVAL; }
+            if (r == cfg.rank) {
+                peer_base[r] = slab;
+            } else if (b.pid == (long long)getpid()) {      // same process: plain peer access
+                int can = 0;
+                SWE_CUDA(cudaDeviceCanAccessPeer(&can, cfg.device, b.device));
+                if (!can && b.device != cfg.device) { err = "no peer access between the devices"; return SWE_B200_ECUDA; }
+                if (b.device != cfg.device) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                        err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                        return SWE_B200_ECUDA;
+                    }
+                    cudaGetLastError();
+                }
+                peer_base[r] = (char*)b.base;
+            } else {
+                void* ptr = nullptr;
+                SWE_CUDA(cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess));
+                peer_base[r] = (char*)ptr;
+                peer_ipc[r] = true;
+            }
+            peer_Ny[r] = b.Ny; peer_plane[r] = b.plane; peer_vol_bytes[r] = b.vol_bytes;
+            peer_mbox[r] = (Mailbox*)(peer_base[r] + b.mbox_offset);
+        }
+        peers_open = true;
+        return SWE_B200_OK;
+    }
+    int check_timeout() {
+        if (!peers_open) return SWE_B200_OK;
+        unsigned long long t = 0;
+        SWE_CUDA(cudaMemcpyAsync(&t, &mbox->timeout, sizeof(t), cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        if (t) { err = "multi-GPU exchange timed out waiting for a neighbour"; return SWE_B200_ECUDA; }
+        return SWE_B200_OK;
+    }
     int64_t launch_count() const override { return launches; }
 };
 

@@ -1,0 +1,135 @@
+// kernels_exchange.cuh -- multi-GPU y-strip exchange over NVLink peer memory (one process per GPU).
+//
+// The reference is single-device; the decomposition is new.  Per RK2 step each rank
+//   * pushes the 2 outermost owned rows of dU (after K1) and of U^{n+1} (after K2 + BC) straight into
+//     the ghost rows of its y-neighbours' buffers with peer stores (no staging, no host involvement),
+//   * all-gathers the two directional CFL maxima through 8-byte mailbox slots in every peer,
+// and the consumers (k_ctl_dt / k_ctl_begin) spin on monotonically increasing stamps written after a
+// system-scope fence.  Every wait has a time-out so a dead peer cannot hang the GPU.
+#pragma once
+#include "kernels_unfused.cuh"
+
+namespace swe {
+
+constexpr int MAX_RANKS = 8;
+
+struct Mailbox {
+    unsigned long long speed[2][MAX_RANKS][2];     // [parity][rank][dir] bit patterns of the local maxima
+    unsigned long long speed_stamp[2][MAX_RANKS];  // step sequence number the slot belongs to
+    unsigned long long halo_stamp[4];              // 0: dU from lower, 1: dU from upper, 2: U from lower, 3: U from upper
+    unsigned long long timeout;                    // != 0: a wait gave up (reported by the host as an error)
+};
+
+template <class S>
+struct PushArgs {
+    const S* src;            // local volume (3 planes)
+    S* dst_lo;               // lower neighbour's volume (peer pointer) or nullptr
+    S* dst_hi;               // upper neighbour's volume (peer pointer) or nullptr
+    long long src_plane, lo_plane, hi_plane;
+    int Nx, Ny, gc, lo_Ny;   // lo_Ny: total rows of the lower neighbour's strip
+    int rows;                // 0: no halo rows (speeds only)
+    unsigned long long* flag_lo;   // in the lower neighbour's mailbox: "from upper" stamp
+    unsigned long long* flag_hi;   // in the upper neighbour's mailbox: "from lower" stamp
+    unsigned long long stamp;
+    int with_speed, nranks, rank;
+    unsigned long long seq;
+    const Ctl* ctl;
+    Mailbox* mbox[MAX_RANKS];      // every rank's mailbox (own included)
+    unsigned int* ticket;          // local counter for last-block detection
+};
+
+template <class S>
+__global__ void k_halo_push(const PushArgs<S> a) {
+    const long long per_side = (long long)a.rows * a.Nx;        // elements per plane and side
+    const long long total = per_side * 3 * 2;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+         q += (long long)gridDim.x * blockDim.x) {
+        const int side = (int)(q / (per_side * 3));
+        const long long r = q - side * per_side * 3;
+        const int k = (int)(r / per_side);
+        const long long e = r - k * per_side;                   // row-major within the gc rows
+        if (side == 0) {   // my lowest owned rows -> lower neighbour's top ghost rows
+            if (a.dst_lo) a.dst_lo[k * a.lo_plane + (long long)(a.lo_Ny - a.gc) * a.Nx + e] =
+                              a.src[k * a.src_plane + (long long)a.gc * a.Nx + e];
+        } else {           // my highest owned rows -> upper neighbour's bottom ghost rows
+            if (a.dst_hi) a.dst_hi[k * a.hi_plane + e] =
+                              a.src[k * a.src_plane + (long long)(a.Ny - 2 * a.gc) * a.Nx + e];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *a.ticket = 0;
+    __threadfence_system();
+    if (a.rows > 0) {
+        if (threadIdx.x == 0 && a.flag_lo) *(volatile unsigned long long*)a.flag_lo = a.stamp;
+        if (threadIdx.x == 1 && a.flag_hi) *(volatile unsigned long long*)a.flag_hi = a.stamp;
+    }
+    if (a.with_speed && threadIdx.x < a.nranks) {
+        Mailbox* m = a.mbox[threadIdx.x];
+        const int par = (int)(a.seq & 1ull);
+        m->speed[par][a.rank][0] = a.ctl->maxspeed_bits[0];
+        m->speed[par][a.rank][1] = a.ctl->maxspeed_bits[1];
+        __threadfence_system();
+        *(volatile unsigned long long*)&m->speed_stamp[par][a.rank] = a.seq;
+    }
+}
+
+__device__ __forceinline__ bool spin_until(volatile unsigned long long* p, unsigned long long want, Mailbox* mb) {
+    const long long t0 = clock64();
+    while (*p < want) {
+        __nanosleep(64);
+        if (clock64() - t0 > 6000000000ll) {   // ~3 s at 2 GHz
+            mb->timeout = 1;
+            return false;
+        }
+    }
+    return true;
+}
+
+// wait for the neighbours' rows of kind `base` (0: dU, 2: U) to have arrived
+__device__ __forceinline__ void wait_halo(Mailbox* mb, int base, int has_lo, int has_hi, unsigned long long stamp) {
+    if (has_lo) spin_until(&mb->halo_stamp[base + 0], stamp, mb);
+    if (has_hi) spin_until(&mb->halo_stamp[base + 1], stamp, mb);
+    __threadfence_system();
+}
+
+static __global__ void k_wait_halo(Mailbox* mb, int base, int has_lo, int has_hi, unsigned long long stamp) {
+    wait_halo(mb, base, has_lo, has_hi, stamp);
+}
+
+// multi-rank timestep: gather all ranks' maxima from the mailbox, then timestep_computer as in k_ctl_dt,
+// then wait for the dU halo rows stage 2 needs.
+template <class S>
+__global__ void k_ctl_dt_multi(Ctl* c, Mailbox* mb, double dx, double dy, S cfl, int nranks, unsigned long long seq,
+                               int has_lo, int has_hi, unsigned long long dU_stamp) {
+    const int par = (int)(seq & 1ull);
+    unsigned long long bx = 0ull, by = 0ull;
+    for (int r = 0; r < nranks; ++r) {
+        spin_until(&mb->speed_stamp[par][r], seq, mb);
+        const unsigned long long x = *(volatile unsigned long long*)&mb->speed[par][r][0];
+        const unsigned long long y = *(volatile unsigned long long*)&mb->speed[par][r][1];
+        bx = x > bx ? x : bx;
+        by = y > by ? y : by;
+    }
+    c->maxspeed_bits[0] = bx;
+    c->maxspeed_bits[1] = by;
+    const S ax = Bits<S>::dec(bx);
+    const S ay = Bits<S>::dec(by);
+    double ddt = fmin(dx / ax, dy / ay);
+    double max_dt = c->max_dt_host;
+    if (c->use_t_end) max_dt = c->match_endtime ? (c->t_end - c->t) : (double)INFINITY;
+    if (c->max_timestep > 0) max_dt = fmin(max_dt, c->max_timestep);
+    double dt = fmin(cfl * ddt, max_dt);
+    const bool past_end = c->use_t_end && !(c->t < c->t_end);
+    if (past_end) dt = 0.0;
+    c->dt = dt;
+    c->dt_s = (double)(S)dt;
+    if (!past_end) c->dt_report = c->dt_s;
+    if (dU_stamp) wait_halo(mb, 0, has_lo, has_hi, dU_stamp);
+}
+
+}  // namespace swe

@@ -1,0 +1,157 @@
+"""y-strip domain decomposition of one Simulator over the GPUs of a box.
+
+The reference is single-device; this is the new capability BASELINE.json's config 5 asks for.
+One process per GPU (torchrun): every rank owns ny/P interior rows plus 2 ghost rows per side; the
+x-direction BC is local on every rank, the y-direction BC only on the first / last rank (periodic-y
+becomes an exchange between rank 0 and rank P-1).  The data path never touches the host: the stage
+kernels' neighbours push halo rows and CFL maxima into each other's memory over NVLink
+(csrc/kernels_exchange.cuh); torch.distributed is used ONLY to all-gather the 128-byte window
+descriptors once at start-up (and by tests / bench to gather results).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Sequence
+
+import numpy as np
+
+from . import _lib
+from . import api
+
+IPC_BYTES = 128
+
+
+def partition_rows(ny: int, nranks: int):
+    """Rows [offset, offset+size) of the global interior owned by each rank (sizes differ by at most 1)."""
+    if nranks < 1 or ny < 4 * nranks:
+        raise api.ArgumentError("every strip needs at least 4 interior rows")
+    base, rem = divmod(ny, nranks)
+    sizes = [base + (1 if r < rem else 0) for r in range(nranks)]
+    offsets = [sum(sizes[:r]) for r in range(nranks)]
+    return offsets, sizes
+
+
+def strip_case(case: dict, state: Sequence[np.ndarray], rank: int, nranks: int):
+    """The sub-problem of `rank`: same parameters, its rows of the state, the bathymetry corner rows
+    (owned rows + 2 ghost rows per side + 1) and of the infiltration factor plane."""
+    gc = case.get("gc", 2)
+    ny = case["ny"]
+    offsets, sizes = partition_rows(ny, nranks)
+    y0, n = offsets[rank], sizes[rank]
+    sub = dict(case)
+    sub["ny"] = n
+    B = case.get("B")
+    if B is not None and not np.isscalar(B):
+        sub["B"] = np.ascontiguousarray(np.asarray(B)[y0:y0 + n + 2 * gc + 1])
+    infil = case.get("infiltration")
+    if isinstance(infil, dict) and not np.isscalar(infil.get("factor", 1.0)):
+        f = dict(infil)
+        f["factor"] = np.ascontiguousarray(np.asarray(infil["factor"])[y0:y0 + n + 2 * gc])
+        sub["infiltration"] = f
+    sub_state = tuple(np.ascontiguousarray(np.asarray(a)[y0:y0 + n]) for a in state)
+    return sub, sub_state, y0, n
+
+
+def _blob(sim: api.Simulator) -> bytes:
+    buf = (C.c_ubyte * IPC_BYTES)()
+    sim._check(_lib.lib().swe_b200_get_ipc_handle(sim._h, buf))
+    return bytes(buf)
+
+
+def _open(sim: api.Simulator, blobs: List[bytes]):
+    raw = b"".join(blobs)
+    buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+    sim._check(_lib.lib().swe_b200_open_peers(sim._h, buf))
+
+
+class StripSimulator:
+    """This rank's strip of a global Simulator (one process per GPU).  `all_gather(bytes) -> [bytes]*P`
+    is any host-side all-gather (see `torch_all_gather`).  Build it from the global problem
+    (`from_global`) or from an already cut strip (constructor)."""
+
+    def __init__(self, sub_case: dict, sub_state, rank: int, nranks: int, global_ny: int, y_offset: int,
+                 all_gather: Callable[[bytes], List[bytes]], device: int = 0, strict: bool = False):
+        self.rank, self.nranks = rank, nranks
+        self.y0, self.ny, self.global_ny = y_offset, sub_case["ny"], global_ny
+        self.sim = api.simulator_from_case(sub_case, strict=strict, fused=True, device=device, rank=rank,
+                                           nranks=nranks, global_ny=global_ny, y_offset=y_offset)
+        if nranks > 1:
+            _open(self.sim, all_gather(_blob(self.sim)))
+        self.sim.set_state_interior(*sub_state)      # collective: pushes the first halo rows to the neighbours
+
+    @classmethod
+    def from_global(cls, case: dict, state, rank: int, nranks: int, all_gather, device: int = 0, strict: bool = False):
+        sub, sub_state, y0, _ = strip_case(case, state, rank, nranks)
+        return cls(sub, sub_state, rank, nranks, case["ny"], y0, all_gather, device=device, strict=strict)
+
+    def run_steps(self, n, maximum_timestep=None):
+        self.sim.run_steps(n, maximum_timestep)
+
+    def run_steps_timed(self, n, maximum_timestep=None):
+        return self.sim.run_steps_timed(n, maximum_timestep)
+
+    def simulate_to_time(self, T, match_endtime=True, maximum_timestep=None):
+        return api.simulate_to_time(self.sim, T, match_endtime=match_endtime, maximum_timestep=maximum_timestep)
+
+    def local_interior(self):
+        return self.sim.get_state_interior()
+
+
+def torch_all_gather(payload: bytes) -> List[bytes]:
+    """all-gather of a small byte string over the default torch.distributed process group"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().tolist()) for t in out]
+
+
+class LocalStripGroup:
+    """All strips inside ONE process, one per visible device (used by tests and single-process runs).
+    Kernels of different strips wait for each other on the GPUs, so only the asynchronous entry points
+    (run_steps) may be used before `sync()`."""
+
+    def __init__(self, case: dict, state, devices: Sequence[int], strict: bool = False):
+        P = len(devices)
+        self.case = case
+        self.sims, self.rows = [], []
+        subs = []
+        for r, dev in enumerate(devices):
+            sub, sub_state, y0, n = strip_case(case, state, r, P)
+            self.sims.append(api.simulator_from_case(sub, strict=strict, fused=True, device=dev, rank=r, nranks=P,
+                                                     global_ny=case["ny"], y_offset=y0))
+            subs.append(sub_state)
+            self.rows.append((y0, n))
+        if P > 1:
+            blobs = [_blob(s) for s in self.sims]
+            for s in self.sims:
+                _open(s, blobs)
+        for s, st in zip(self.sims, subs):
+            s.set_state_interior(*st)
+
+    def run_steps(self, n, maximum_timestep=None):
+        # interleave so that no rank's launch queue runs far ahead of its neighbours
+        for _ in range(int(n)):
+            for s in self.sims:
+                s.run_steps(1, maximum_timestep)
+
+    def sync(self):
+        for s in self.sims:
+            s.sync()
+
+    def gather_interior(self):
+        self.sync()
+        parts = [s.get_state_interior() for s in self.sims]
+        return [np.concatenate([p[k] for p in parts], axis=0) for k in range(3)]
+
+    @property
+    def t(self):
+        return self.sims[0].t
+
+    @property
+    def dt(self):
+        return self.sims[0].dt

@@ -34,7 +34,7 @@ def cell_centers(n: int, gc: int, lo: float, hi: float, interior: bool = True) -
 
 def terrain_corners(nx: int, ny: int, gc: int = 2, extent=None, seed: int = 1234,
                     amplitude: float = None, wavelength: float = 512.0, slope: float = 0.0,
-                    depression: float = None, dtype=np.float32, octaves: int = 5) -> np.ndarray:
+                    depression: float = None, dtype=np.float32, octaves: int = 5, row_range=None) -> np.ndarray:
     """Smooth hills (sum of `octaves` separable sinusoid products with seeded phases) + a linear
     slope in x + one bay-like Gaussian depression.  Evaluated at the (nx+2gc+1) x (ny+2gc+1) cell
     corners (incl. ghost region), as BottomTopography2D expects (bottom_topography.jl:51-59).
@@ -65,6 +65,8 @@ def terrain_corners(nx: int, ny: int, gc: int = 2, extent=None, seed: int = 1234
     by.append(np.exp(-((y - (extent[2] + 0.4 * Ly)) ** 2) / s2y))
     A = np.stack(ax, axis=0).astype(dtype)      # (K, Nx+1)
     Bm = np.stack(by, axis=1).astype(dtype)     # (Ny+1, K)
+    if row_range is not None:                   # only the corner rows [r0, r1) (a y-strip of the field)
+        Bm = Bm[row_range[0]:row_range[1]]
     return np.ascontiguousarray(Bm @ A)          # (Ny+1, Nx+1)
 
 
@@ -92,11 +94,13 @@ def cell_average(Bc: np.ndarray) -> np.ndarray:
     return 0.25 * s.astype(np.float64)
 
 
-def lake_initial_state(Bc: np.ndarray, gc: int, level: float, hump: float = 0.5, dtype=np.float32):
-    """w = max(B_cell, level) plus a Gaussian hump on the wet part; hu = hv = 0.  Interior only."""
+def lake_initial_state(Bc: np.ndarray, gc: int, level: float, hump: float = 0.5, dtype=np.float32,
+                       y_offset: int = 0, ny_global: int = None):
+    """w = max(B_cell, level) plus a Gaussian hump on the wet part; hu = hv = 0.  Interior only.
+    With y_offset / ny_global, Bc is the corner strip of the rows [y_offset, y_offset + ny) of a taller grid."""
     Bcell = cell_average(Bc)[gc:-gc, gc:-gc]
     ny, nx = Bcell.shape
-    y = (np.arange(ny) + 0.5) / ny
+    y = (y_offset + np.arange(ny) + 0.5) / (ny_global if ny_global is not None else ny)
     x = (np.arange(nx) + 0.5) / nx
     bump = hump * np.exp(-((x[None, :] - 0.6) ** 2 + (y[:, None] - 0.4) ** 2) / 0.01)
     w = np.maximum(Bcell, level + bump)
