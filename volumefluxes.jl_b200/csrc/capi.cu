@@ -2,6 +2,8 @@
 #include <cstring>
 #include <string>
 
+#include <cuda_runtime.h>
+
 #include "engine.h"
 
 struct swe_b200_handle {
@@ -50,6 +52,7 @@ int swe_b200_create(const swe_b200_config* c, swe_b200_handle** out) {
 
 int swe_b200_destroy(swe_b200_handle* h) {
     if (!h) return SWE_B200_EINVAL;
+    if (h->e) cudaSetDevice(h->e->device());
     delete h->e;
     delete h;
     return SWE_B200_OK;
@@ -59,7 +62,8 @@ const char* swe_b200_last_error(swe_b200_handle* h) {
     if (h->e && !h->e->err.empty()) h->last = h->e->err;
     return h->last.c_str();
 }
-#define FWD(call) do { H_OR_FAIL(h); int rc_ = h->e->call; return rc_ ? fail(h, rc_) : rc_; } while (0)
+// every entry point runs with the handle's device current (several handles / devices per process are fine)
+#define FWD(call) do { H_OR_FAIL(h); cudaSetDevice(h->e->device()); int rc_ = h->e->call; return rc_ ? fail(h, rc_) : rc_; } while (0)
 
 int swe_b200_sync(swe_b200_handle* h) { FWD(sync()); }
 int swe_b200_set_bathymetry(swe_b200_handle* h, const void* B, int64_t n) { FWD(set_bathymetry(B, n)); }

@@ -35,6 +35,7 @@ struct Engine {
     virtual int get_ipc_handle(void* handle64) = 0;
     virtual int open_peers(const void* all_handles64) = 0;
     virtual int64_t launch_count() const = 0;
+    virtual int device() const = 0;
 };
 
 // factories, one per translation unit / arithmetic policy family

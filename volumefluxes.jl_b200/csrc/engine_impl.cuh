@@ -668,6 +668,7 @@ public:
         return SWE_B200_OK;
     }
     int64_t launch_count() const override { return launches; }
+    int device() const override { return cfg.device; }
 };
 
 template <class P>
