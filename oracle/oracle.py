@@ -97,6 +97,11 @@ def lib():
         L.orc_enumerate_ghost_cells.argtypes = [vp, i32, vp]
         L.orc_enumerate_cells.restype = i64
         L.orc_enumerate_cells.argtypes = [vp, vp]
+        L.orc_zero.argtypes = [vp, i32]
+        L.orc_axpy.argtypes = [vp, i32, i32, dbl, i32]
+        L.orc_rk_average.argtypes = [vp, i32, i32]
+        L.orc_update_bc_sides.argtypes = [vp, i32, i32, i32, i32, i32]
+        L.orc_rotate.argtypes = [vp]
         L.orc_set_threads.restype = i32
         L.orc_set_threads.argtypes = [i32]
         _lib = L
@@ -260,6 +265,22 @@ class OracleSim:
 
     def post_proc(self, which):
         lib().orc_post_proc(self._h, which)
+
+    # pieces of do_substep! / perform_step! for host-driven (y-strip) runs
+    def zero(self, which):
+        lib().orc_zero(self._h, which)
+
+    def axpy(self, out_buffer, state_buffer, dt, rounded=False):
+        lib().orc_axpy(self._h, out_buffer, state_buffer, float(dt), 1 if rounded else 0)
+
+    def rk_average(self, out_buffer, first_buffer=0):
+        lib().orc_rk_average(self._h, out_buffer, first_buffer)
+
+    def update_bc_sides(self, which, xlo=True, xhi=True, ylo=True, yhi=True):
+        lib().orc_update_bc_sides(self._h, which, int(xlo), int(xhi), int(ylo), int(yhi))
+
+    def rotate(self):
+        lib().orc_rotate(self._h)
 
     # -- scalars / index spaces ---------------------------------------------------------------
     def B_cell(self, i, j=1):

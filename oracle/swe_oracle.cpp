@@ -423,7 +423,8 @@ struct Oracle {
     }
 
     // ---- bc.jl:22-114 ; ghost iteration space grid.jl:246-253 ------------------------------
-    void update_bc_dir(std::vector<S>& d, int dir) {
+    // lo / hi: apply the BC on the low / high side (false on a y-strip side owned by a neighbour rank)
+    void update_bc_dir(std::vector<S>& d, int dir, bool lo = true, bool hi = true) {
         const int64_t gc = c.gc;
         const int64_t N = dir == 0 ? Nx : Ny;         // totalcells[dir]
         int64_t p0, p1;                                // passive range (interior)
@@ -438,16 +439,18 @@ struct Oracle {
             for (int64_t g = 1; g <= gc; ++g) {        // sequential order: g fastest (CPU backend)
                 for (int k = 0; k < nvar; ++k) {
                     if (c.bc == 0) {                   // PeriodicBC :22-40
-                        d[idx(g, p, k)] = d[idx(N + g - 2 * gc, p, k)];
-                        d[idx(N - (gc - g), p, k)] = d[idx(gc + g, p, k)];
+                        if (lo) d[idx(g, p, k)] = d[idx(N + g - 2 * gc, p, k)];
+                        if (hi) d[idx(N - (gc - g), p, k)] = d[idx(gc + g, p, k)];
                     } else if (c.bc == 2) {            // NeumannBC :42-60 (reference quirks kept)
-                        if (c.dim == 1 || dir == 0) d[idx(g, p, k)] = d[idx(2 * gc - g + 1, p, k)];
-                        else d[idx(g, p, k)] = d[idx(N + g - 2 * gc, p, k)];
-                        d[idx(N - (gc - g), p, k)] = d[idx(N - g + 1, p, k)];
+                        if (lo) {
+                            if (c.dim == 1 || dir == 0) d[idx(g, p, k)] = d[idx(2 * gc - g + 1, p, k)];
+                            else d[idx(g, p, k)] = d[idx(N + g - 2 * gc, p, k)];
+                        }
+                        if (hi) d[idx(N - (gc - g), p, k)] = d[idx(N - g + 1, p, k)];
                     } else {                           // WallBC :63-110
                         const S sgn = (k == normal) ? (S)-1 : (S)1;
-                        d[idx(g, p, k)] = sgn * d[idx(gc * 2 + 1 - g, p, k)];
-                        d[idx(N - gc + g, p, k)] = sgn * d[idx(N - gc - g + 1, p, k)];
+                        if (lo) d[idx(g, p, k)] = sgn * d[idx(gc * 2 + 1 - g, p, k)];
+                        if (hi) d[idx(N - gc + g, p, k)] = sgn * d[idx(N - gc - g + 1, p, k)];
                     }
                 }
             }
@@ -653,6 +656,52 @@ int orc_implicit_friction(void* hp, int out_buffer, int prev_buffer, double dt) 
         o.implicit_friction(o.vol[o.cur[out_buffer]], o.vol[o.cur[prev_buffer]], (S)dt);
         return 0;
     });
+}
+// ---- pieces of do_substep!/perform_step! exposed one by one, so that a host-side driver can run a
+// y-strip decomposition (global dt, halo rows from neighbours) with exactly the reference arithmetic ----
+int orc_zero(void* hp, int which) {
+    return dispatch(hp, [&](auto& o) {
+        using S = typename std::remove_reference<decltype(o.ws[0])>::type;
+        std::fill(o.vol[o.cur[which]].begin(), o.vol[o.cur[which]].end(), (S)0);
+        return 0;
+    });
+}
+// out = state + dt*out ; rounded != 0: dt is the realtype value of stage 2 (rungekutta.jl:39-41)
+int orc_axpy(void* hp, int out_buffer, int state_buffer, double dt, int rounded) {
+    return dispatch(hp, [&](auto& o) {
+        using S = typename std::remove_reference<decltype(o.ws[0])>::type;
+        auto& out = o.vol[o.cur[out_buffer]];
+        const auto& st = o.vol[o.cur[state_buffer]];
+        const int64_t n = (int64_t)out.size();
+        if (rounded) {
+            const S dts = (S)dt;
+            for (int64_t q = 0; q < n; ++q) out[q] = (S)(st[q] + dts * out[q]);
+        } else {
+            for (int64_t q = 0; q < n; ++q) out[q] = (S)(st[q] + dt * out[q]);
+        }
+        return 0;
+    });
+}
+// out = 0.5*(first + out) (rungekutta.jl:46-48)
+int orc_rk_average(void* hp, int out_buffer, int first_buffer) {
+    return dispatch(hp, [&](auto& o) {
+        using S = typename std::remove_reference<decltype(o.ws[0])>::type;
+        auto& out = o.vol[o.cur[out_buffer]];
+        const auto& f = o.vol[o.cur[first_buffer]];
+        for (size_t q = 0; q < out.size(); ++q) out[q] = (S)(0.5 * (f[q] + out[q]));
+        return 0;
+    });
+}
+int orc_update_bc_sides(void* hp, int which, int xlo, int xhi, int ylo, int yhi) {
+    return dispatch(hp, [&](auto& o) {
+        o.update_bc_dir(o.vol[o.cur[which]], 0, xlo != 0, xhi != 0);
+        if (o.c.dim == 2) o.update_bc_dir(o.vol[o.cur[which]], 1, ylo != 0, yhi != 0);
+        return 0;
+    });
+}
+// simulator.jl:175-176
+int orc_rotate(void* hp) {
+    return dispatch(hp, [&](auto& o) { std::swap(o.cur[0], o.cur[o.nsub()]); return 0; });
 }
 int orc_post_proc(void* hp, int which) {
     return dispatch(hp, [&](auto& o) { o.post_proc(o.vol[o.cur[which]]); return 0; });
