@@ -10,8 +10,12 @@
 #include "engine.h"
 #include <unistd.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "kernels_exchange.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_fused_x2.cuh"
 
 namespace swe {
 
@@ -44,6 +48,9 @@ public:
     swe_b200_config cfg;
     Par<C> par;
     int Nx, Ny, gc;
+    int Bp = 0;             // internal pitch of the corner bathymetry: Nx+1 rounded up to even (64-bit loads)
+    bool x2_ok = false;     // Float32 fast policy: the packed two-column stage kernels (kernels_fused_x2.cuh)
+    x2::Par2 par2;
     long long plane;
     cudaStream_t stream = nullptr;
     S* vol[3] = {nullptr, nullptr, nullptr};
@@ -81,6 +88,7 @@ public:
         Nx = c.nx + 2 * gc;
         Ny = c.ny + 2 * gc;
         plane = (long long)Nx * Ny;
+        Bp = (Nx + 2) / 2 * 2;
         SWE_CUDA(cudaSetDevice(c.device));
         SWE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         const int gny = c.global_ny > 0 ? c.global_ny : c.ny;
@@ -117,8 +125,8 @@ public:
             hi_rank = c.rank < c.nranks - 1 ? c.rank + 1 : (per ? 0 : -1);
         }
         if (c.has_bathymetry) {
-            SWE_CUDA(cudaMalloc(&B, sizeof(S) * (size_t)(Nx + 1) * (Ny + 1)));
-            SWE_CUDA(cudaMemsetAsync(B, 0, sizeof(S) * (size_t)(Nx + 1) * (Ny + 1), stream));
+            SWE_CUDA(cudaMalloc(&B, sizeof(S) * (size_t)Bp * (Ny + 1)));
+            SWE_CUDA(cudaMemsetAsync(B, 0, sizeof(S) * (size_t)Bp * (Ny + 1), stream));
         }
         if (c.infil_kind == SWE_B200_INFIL_HORTON) {
             SWE_CUDA(cudaMalloc(&factor, sizeof(double) * plane));
@@ -136,6 +144,7 @@ public:
         ip.kind = c.infil_kind; ip.cst = c.infil_const; ip.f0 = c.f0; ip.fc = c.fc; ip.k = c.k;
         // the fused stage kernels cover the practical 2D SWE with gc == 2 and periodic / wall BCs
         fused_ok = c.fused && c.eq_kind == 0 && gc == 2 && c.bc != SWE_B200_BC_NEUMANN && c.nx >= 4 && c.ny >= 4;
+        setup_x2(c);
         if (multi && !fused_ok) {
             err = "y-strip decomposition needs the fused path (ShallowWaterEquations, gc == 2, periodic/wall BC)";
             return SWE_B200_EUNSUPPORTED;
@@ -154,6 +163,48 @@ public:
         if (stream) cudaStreamDestroy(stream);
     }
 
+    // Float32 fast policy only: parameters of the packed two-column kernels.  Needs an even row pitch
+    // (64-bit loads), cutoff >= 0 and kappa > 0 (the input-side dry mask assumes a non-negative wet depth).
+    void setup_x2(const swe_b200_config& c) {
+        x2_ok = false;
+        if (!std::is_same<P, Policy<float, float, false>>::value) return;
+        const char* off = std::getenv("SWE_B200_NO_X2");
+        if (off && off[0] == '1') return;
+        if (!fused_ok || (Nx & 1) || !(c.depth_cutoff >= 0) || !(c.kappa > 0)) return;
+        const int gny = c.global_ny > 0 ? c.global_ny : c.ny;
+        const double dx = (c.extent[1] - c.extent[0]) / c.nx, dy = (c.extent[3] - c.extent[2]) / gny;
+        auto s2 = [](double v) { return make_float2((float)v, (float)v); };
+        x2::Par2& q = par2;
+        q.Nx = Nx; q.Ny = Ny; q.plane = plane; q.Bp = Bp;
+        q.bc = c.bc; q.friction = c.friction; q.bottom_source = c.has_bottom_source;
+        q.ylo_phys = par.ylo_phys; q.yhi_phys = par.yhi_phys;
+        q.rain_kind = c.rain_kind; q.infil_kind = c.infil_kind; q.infil_first = c.infil_first; q.rows = x2::ROWS;
+        q.cutoff = (float)c.depth_cutoff; q.kappa = (float)c.kappa; q.constB = (float)c.const_B;
+        q.theta = s2(c.theta); q.half = s2(0.5); q.mhalf = s2(-0.5); q.quarter = s2(0.25);
+        q.g = s2(c.g); q.K = s2(0.5 * c.rho * c.g); q.i2k = s2(1.0 / (2 * c.kappa)); q.hk = s2(c.kappa / 2.0);
+        q.rho = s2(c.rho); q.nrdx = s2(-1.0 / dx); q.nrdy = s2(-1.0 / dy);
+        q.botx = s2(-0.25 * c.g / dx); q.boty = s2(-0.25 * c.g / dy); q.Cz = s2(c.Cz);
+        x2_ok = true;
+    }
+    template <int STAGE>
+    void launch_stage_x2(const S* U, const S* D, S* out) {
+        if constexpr (std::is_same<P, Policy<float, float, false>>::value) {
+            x2::Args2 a;
+            a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl;
+            const int ntiles = (cfg.nx + x2::VW - 1) / x2::VW;
+            dim3 g((ntiles + x2::WPB - 1) / x2::WPB, (cfg.ny + a.p.rows - 1) / a.p.rows);
+            dim3 b(x2::WPB * 32);
+            const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
+            if (B) {
+                if (lin) x2::k_stage_x2<1, true, STAGE><<<g, b, 0, stream>>>(a);
+                else x2::k_stage_x2<0, true, STAGE><<<g, b, 0, stream>>>(a);
+            } else {
+                if (lin) x2::k_stage_x2<1, false, STAGE><<<g, b, 0, stream>>>(a);
+                else x2::k_stage_x2<0, false, STAGE><<<g, b, 0, stream>>>(a);
+            }
+        }
+    }
+
     // ------------------------------------------------------------------------------------------
     int check() {
         cudaError_t e = cudaGetLastError();
@@ -170,7 +221,7 @@ public:
         SWE_CUDA(cudaMemsetAsync(ws, 0, sizeof(S) * plane, stream));
         return SWE_B200_OK;
     }
-    Bathy<P> bathy() const { return Bathy<P>{B, Nx + 1, par.constB}; }
+    Bathy<P> bathy() const { return Bathy<P>{B, Bp, par.constB}; }
     dim3 blk2() const { return dim3(32, 8); }
     dim3 grd2() const { return dim3((Nx + 31) / 32, (Ny + 7) / 8); }
     int grd1(long long n) const { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
@@ -187,7 +238,8 @@ public:
             err = "Bottom topography should be of size (" + std::to_string(Nx + 1) + ", " + std::to_string(Ny + 1) + ")";
             return SWE_B200_EDOMAIN;
         }
-        SWE_CUDA(cudaMemcpyAsync(B, Bh, sizeof(S) * n, cudaMemcpyHostToDevice, stream));
+        SWE_CUDA(cudaMemcpy2DAsync(B, sizeof(S) * Bp, Bh, sizeof(S) * (Nx + 1), sizeof(S) * (Nx + 1), Ny + 1,
+                                   cudaMemcpyHostToDevice, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
         return SWE_B200_OK;
     }
@@ -416,7 +468,7 @@ public:
     template <int STAGE>
     void launch_stage(const S* U, const S* D, S* out) {
         StageArgs<P> a;
-        a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl;
+        a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.Bp = Bp; a.factor = factor; a.ctl = ctl;
         a.rain_kind = cfg.rain_kind; a.infil_kind = cfg.infil_kind; a.infil_first = cfg.infil_first;
         a.rows = FUSED_ROWS;
         const int nwarps = (cfg.nx + FUSED_VW - 1) / FUSED_VW;
@@ -428,7 +480,8 @@ public:
             cudaEventRecord(e0, stream);
         }
         const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
-        if (B) {
+        if (x2_ok) launch_stage_x2<STAGE>(U, D, out);
+        else if (B) {
             if (lin) k_stage<P, 1, true, STAGE><<<g, b, 0, stream>>>(a);
             else k_stage<P, 0, true, STAGE><<<g, b, 0, stream>>>(a);
         } else {

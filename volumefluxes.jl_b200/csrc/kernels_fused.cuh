@@ -35,7 +35,8 @@ struct StageArgs {
     const S* U;        // U^n, ghosts valid
     const S* D;        // dU (stage 2 input)
     S* out;            // stage 1: dU ; stage 2: U^{n+1}
-    const S* B;        // corners (pitch Nx+1) or nullptr
+    const S* B;        // corners (pitch Bp) or nullptr
+    int Bp;
     const double* factor;   // Horton factor plane or nullptr
     Ctl* ctl;
     int rain_kind, infil_kind, infil_first;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
     const bool out_lane = lane >= 2 && lane <= 29 && i < Nx - 2;
     const bool xface_lane = lane >= 1 && lane <= 29 && i >= 1 && i <= Nx - 3;
     const long long plane = p.plane;
-    const int Bp = Nx + 1;
+    const int Bp = a.Bp;
 
     // stage-2 control scalars and x ghost map
     C dt = 0;
