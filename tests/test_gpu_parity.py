@@ -129,15 +129,21 @@ def test_strict_steps_bit_exact(P, oracle, name, dtype, fused):
 FAST_CASES = [n for n in sorted(SMALL_CASES) if n != "lake_step_fe"]   # lake at rest: see test_lake_at_rest_2d
 
 
-def run_oracle(oracle, case, state, n):
+CHECKPOINTS = (20, 100)     # 20 steps: before the dry-state switches decorrelate; 100: the SURVEY 8c protocol
+SENS_SEEDS = (1, 2, 3, 4)   # the oracle's own +-1 ulp sensitivity is heavy-tailed: take the max over seeds
+
+
+def run_oracle(oracle, case, state, checkpoints=CHECKPOINTS):
     o = oracle.OracleSim(case)
     o.set_state_interior(*state)
     mts = case.get("maximum_timestep", math.inf)
-    dts = []
-    for _ in range(n):
+    dts, snaps = [], {}
+    for n in range(1, max(checkpoints) + 1):
         o.step(mts)
         dts.append(o.dt)
-    return interior(o.get_state_full()), np.array(dts)
+        if n in checkpoints:
+            snaps[n] = interior(o.get_state_full()).copy()
+    return snaps, np.array(dts)
 
 
 def wet_mask(case, w):
@@ -148,31 +154,34 @@ def wet_mask(case, w):
 @pytest.mark.parametrize("dtype,tol", [("float64", F64_TOL), ("float32", F32_TOL)])
 @pytest.mark.parametrize("name", FAST_CASES)
 def test_fast_fused_parity_100_steps(P, oracle, name, dtype, tol):
-    N = 100
     case, state = SMALL_CASES[name](dtype)
-    b, dts_o = run_oracle(oracle, case, state, N)
-    bp, dts_p = run_oracle(oracle, case, cases.perturb_ulp(state, dtype), N)
-    sens = cases.field_errors(bp, b)
-    sens_dt = float(np.max(np.abs(dts_p - dts_o) / dts_o))
+    ref, dts_o = run_oracle(oracle, case, state)
+    pert = [run_oracle(oracle, case, cases.perturb_ulp(state, dtype, seed=sd)) for sd in SENS_SEEDS]
     s = P.simulator_from_case(case, strict=False, fused=True)
     s.set_state_interior(*state)
     mts = case.get("maximum_timestep", math.inf)
     dts = []
-    for n in range(N):
+    for n in range(1, max(CHECKPOINTS) + 1):
         s.step(mts)
         dts.append(s.dt)
-    a = interior(s.get_state_full())
-    err = cases.field_errors(a, b)
-    print(f"\n{name} {dtype}: err {['%.1e' % e for e in err]} oracle 1-ulp sensitivity {['%.1e' % e for e in sens]}")
-    for e, sn, nm in zip(err, sens, ("w", "hu", "hv")):
-        assert e <= max(tol, 4 * sn), f"{nm}: rel L-inf {e:.3e} (tolerance {tol:g}, 1-ulp sensitivity {sn:.3e})"
-    err_dt = float(np.max(np.abs(np.array(dts) - dts_o) / dts_o))
-    assert err_dt <= max(tol, 1e-6 if dtype == "float32" else tol, 4 * sens_dt)
-    if case.get("B") is not None and not np.isscalar(case.get("B")):
-        mism = int(np.sum(wet_mask(case, a[0]) != wet_mask(case, b[0])))
-        mism_ref = int(np.sum(wet_mask(case, bp[0]) != wet_mask(case, b[0])))
-        assert mism <= 2 * mism_ref + (0 if max(sens) <= tol else 4), \
-            f"wet/dry masks differ in {mism} cells (1-ulp-perturbed oracle: {mism_ref})"
+        if n not in CHECKPOINTS:
+            continue
+        a, b = interior(s.get_state_full()), ref[n]
+        sens = np.max([cases.field_errors(pp[n], b) for pp, _ in pert], axis=0)
+        sens_dt = max(float(np.max(np.abs(pd[:n] - dts_o[:n]) / dts_o[:n])) for _, pd in pert)
+        err = cases.field_errors(a, b)
+        print(f"\n{name} {dtype} N={n}: err {['%.1e' % e for e in err]} "
+              f"oracle 1-ulp sensitivity {['%.1e' % e for e in sens]}")
+        for e, sn, nm in zip(err, sens, ("w", "hu", "hv")):
+            assert e <= max(tol, 4 * sn), \
+                f"N={n} {nm}: rel L-inf {e:.3e} (tolerance {tol:g}, 1-ulp sensitivity {sn:.3e})"
+        err_dt = float(np.max(np.abs(np.array(dts) - dts_o[:n]) / dts_o[:n]))
+        assert err_dt <= max(tol, 1e-6 if dtype == "float32" else tol, 4 * sens_dt)
+        if case.get("B") is not None and not np.isscalar(case.get("B")):
+            mism = int(np.sum(wet_mask(case, a[0]) != wet_mask(case, b[0])))
+            mism_ref = max(int(np.sum(wet_mask(case, pp[n][0]) != wet_mask(case, b[0]))) for pp, _ in pert)
+            assert mism <= 2 * mism_ref + (0 if max(sens) <= tol else 4), \
+                f"N={n}: wet/dry masks differ in {mism} cells (1-ulp-perturbed oracle: {mism_ref})"
 
 
 @pytest.mark.parametrize("dtype,tol", [("float64", F64_TOL), ("float32", F32_TOL)])
@@ -184,8 +193,8 @@ def test_fast_unfused_matches_fused(P, dtype, tol):
         s.set_state_interior(*state)
         s.run_steps(50, case.get("maximum_timestep"))
     x, y = interior(a.get_state_full()), interior(b.get_state_full())
-    for k in range(3):
-        assert cases.rel_linf(x[k], y[k]) <= tol
+    for k in range(3):      # both are within tol of the oracle, so within 2 tol of each other
+        assert cases.rel_linf(x[k], y[k]) <= 2 * tol
     assert a.t == pytest.approx(b.t, rel=1e-6)
 
 

@@ -164,13 +164,13 @@ public:
     }
 
     // Float32 fast policy only: parameters of the packed two-column kernels.  Needs an even row pitch
-    // (64-bit loads), cutoff >= 0 and kappa > 0 (the input-side dry mask assumes a non-negative wet depth).
+    // (64-bit loads), cutoff >= 0 and 0 < kappa < 1 (input-side dry mask; desingularisation by a saturating add).
     void setup_x2(const swe_b200_config& c) {
         x2_ok = false;
         if (!std::is_same<P, Policy<float, float, false>>::value) return;
         const char* off = std::getenv("SWE_B200_NO_X2");
         if (off && off[0] == '1') return;
-        if (!fused_ok || (Nx & 1) || !(c.depth_cutoff >= 0) || !(c.kappa > 0)) return;
+        if (!fused_ok || (Nx & 1) || !(c.depth_cutoff >= 0) || !(c.kappa > 0) || !(c.kappa < 1)) return;
         const int gny = c.global_ny > 0 ? c.global_ny : c.ny;
         const double dx = (c.extent[1] - c.extent[0]) / c.nx, dy = (c.extent[3] - c.extent[2]) / gny;
         auto s2 = [](double v) { return make_float2((float)v, (float)v); };
@@ -183,11 +183,14 @@ public:
         q.theta = s2(c.theta); q.half = s2(0.5); q.mhalf = s2(-0.5); q.quarter = s2(0.25);
         q.g = s2(c.g); q.K = s2(0.5 * c.rho * c.g); q.i2k = s2(1.0 / (2 * c.kappa)); q.hk = s2(c.kappa / 2.0);
         q.rho = s2(c.rho); q.nrdx = s2(-1.0 / dx); q.nrdy = s2(-1.0 / dy);
-        q.botx = s2(-0.25 * c.g / dx); q.boty = s2(-0.25 * c.g / dy); q.Cz = s2(c.Cz);
+        q.botx = s2(c.has_bottom_source ? -0.25 * c.g / dx : 0.0); q.boty = s2(c.has_bottom_source ? -0.25 * c.g / dy : 0.0); q.Cz = s2(c.Cz);
+        if (const char* e = std::getenv("SWE_B200_X2_ROWS")) q.rows = std::max(3, atoi(e) / 3 * 3);   // multiple of 3
+        if (const char* e = std::getenv("SWE_B200_X2_MINB")) x2_minb = atoi(e);
         x2_ok = true;
     }
-    template <int STAGE>
-    void launch_stage_x2(const S* U, const S* D, S* out) {
+    int x2_minb = 4;        // resident blocks per SM the x2 kernels are compiled for (register cap 96 / 128)
+    template <int STAGE, int MINB>
+    void launch_stage_x2_m(const S* U, const S* D, S* out) {
         if constexpr (std::is_same<P, Policy<float, float, false>>::value) {
             x2::Args2 a;
             a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl;
@@ -195,14 +198,29 @@ public:
             dim3 g((ntiles + x2::WPB - 1) / x2::WPB, (cfg.ny + a.p.rows - 1) / a.p.rows);
             dim3 b(x2::WPB * 32);
             const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
+            const int fr = cfg.friction == SWE_B200_FRICTION_NONE ? 0 : (cfg.friction == SWE_B200_FRICTION_BH2021 ? 1 : 2);
+#define SWE_X2_LAUNCH(R, HB, F) x2::k_stage_x2<R, HB, STAGE, (STAGE == 2 ? F : 0), MINB><<<g, b, 0, stream>>>(a)
+#define SWE_X2_FRIC(R, HB)                                                                   \
+    do {                                                                                     \
+        if (STAGE == 1 || fr == 0) SWE_X2_LAUNCH(R, HB, 0);                                  \
+        else if (fr == 1) SWE_X2_LAUNCH(R, HB, 1);                                           \
+        else SWE_X2_LAUNCH(R, HB, 2);                                                        \
+    } while (0)
             if (B) {
-                if (lin) x2::k_stage_x2<1, true, STAGE><<<g, b, 0, stream>>>(a);
-                else x2::k_stage_x2<0, true, STAGE><<<g, b, 0, stream>>>(a);
+                if (lin) SWE_X2_FRIC(1, true);
+                else SWE_X2_FRIC(0, true);
             } else {
-                if (lin) x2::k_stage_x2<1, false, STAGE><<<g, b, 0, stream>>>(a);
-                else x2::k_stage_x2<0, false, STAGE><<<g, b, 0, stream>>>(a);
+                if (lin) SWE_X2_FRIC(1, false);
+                else SWE_X2_FRIC(0, false);
             }
+#undef SWE_X2_FRIC
+#undef SWE_X2_LAUNCH
         }
+    }
+    template <int STAGE>
+    void launch_stage_x2(const S* U, const S* D, S* out) {
+        if (x2_minb == 4) launch_stage_x2_m<STAGE, 4>(U, D, out);
+        else launch_stage_x2_m<STAGE, 5>(U, D, out);
     }
 
     // ------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ typedef float2 f2;
 
 constexpr int VW = 60;       // valid (output) columns per warp: lanes 1..30, two columns each
 constexpr int WPB = 4;       // warps per block
-constexpr int ROWS = 64;     // rows marched per block
+constexpr int ROWS = 66;     // rows marched per block
 
 __device__ __forceinline__ f2 mk(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ f2 sp(float a) { return make_float2(a, a); }
@@ -84,6 +84,21 @@ __device__ __forceinline__ float minmod3f(float a, float b, float c) {
 
 // ---- reconstruction of a pair of cells from the centre values and the backward / forward differences
 // (linearreconstruction.jl:37-43, 73-100; noreconstruction.jl:30-46).  tBl/tBr = 2 * face bathymetry.
+// faces2: slope clamp of w (no negative face depth), face values, depth = w - face bathymetry
+__device__ __forceinline__ void faces2(const Par2& p, const f2 c[3], f2 s[3], f2 tBl, f2 tBr, f2 L[3], f2 R[3]) {
+    const f2 w2 = add(c[0], c[0]);
+    const f2 s1 = sub(w2, tBl), s2 = sub(tBr, w2);
+    s[0].x = s[0].x > s1.x ? s1.x : fmaxf(s[0].x, s2.x);
+    s[0].y = s[0].y > s1.y ? s1.y : fmaxf(s[0].y, s2.y);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        L[k] = fma2(s[k], p.mhalf, c[k]);
+        R[k] = fma2(s[k], p.half, c[k]);
+    }
+    L[0] = fma2(tBl, p.mhalf, L[0]);
+    R[0] = fma2(tBr, p.mhalf, R[0]);
+}
+// y direction: the backward / forward differences are pairs of the same two columns
 template <int RECON>
 __device__ __forceinline__ void recon2(const Par2& p, const f2 c[3], const f2 bwd[3], const f2 fwd[3], f2 tBl, f2 tBr,
                                        f2 Bc, f2 L[3], f2 R[3]) {
@@ -100,17 +115,37 @@ __device__ __forceinline__ void recon2(const Par2& p, const f2 c[3], const f2 bw
         const f2 cen = mul(p.half, add(fwd[k], bwd[k]));
         s[k] = mk(minmod3f(tf.x, cen.x, tb.x), minmod3f(tf.y, cen.y, tb.y));
     }
-    const f2 w2 = add(c[0], c[0]);
-    const f2 s1 = sub(w2, tBl), s2 = sub(tBr, w2);
-    s[0].x = s[0].x > s1.x ? s1.x : fmaxf(s[0].x, s2.x);
-    s[0].y = s[0].y > s1.y ? s1.y : fmaxf(s[0].y, s2.y);
+    faces2(p, c, s, tBl, tBr, L, R);
+}
+// x direction: the two cells of a thread are neighbours, so the three differences d0 = a - left, d1 = b - a,
+// d2 = right - b are shared; everything is built from scalars that land in aligned pairs (no pair shuffling).
+template <int RECON>
+__device__ __forceinline__ void recon2x(const Par2& p, const f2 c[3], const float ql[3], const float qr[3], f2 tBl,
+                                        f2 tBr, f2 Bc, f2 L[3], f2 R[3]) {
+    if (RECON == 0) {
+        L[0] = R[0] = sub(c[0], Bc);
+        L[1] = R[1] = c[1];
+        L[2] = R[2] = c[2];
+        return;
+    }
+    f2 s[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        L[k] = fma2(s[k], p.mhalf, c[k]);
-        R[k] = fma2(s[k], p.half, c[k]);
+        const f2 d01 = mk(c[k].x - ql[k], c[k].y - c[k].x);               // (d0, d1)
+        const float d2 = qr[k] - c[k].y;
+        const f2 t01 = mul(p.theta, d01);
+        const float t2 = p.theta.x * d2;
+        const f2 cen = mul(p.half, mk(c[k].y - ql[k], qr[k] - c[k].x));    // ((d0+d1)/2, (d1+d2)/2)
+        s[k] = mk(minmod3f(t01.y, cen.x, t01.x), minmod3f(t2, cen.y, t01.y));
     }
-    L[0] = fma2(tBl, p.mhalf, L[0]);
-    R[0] = fma2(tBr, p.mhalf, R[0]);
+    faces2(p, c, s, tBl, tBr, L, R);
+}
+
+// desingularised depth of a NON-NEGATIVE depth pair (equation.jl:56-62): max(h, min(h^2/2k + k/2, k)) is
+// h + relu(k - h)^2 / 2k; k - h <= k < 1, so the relu is one saturating add on the FMA pipe.
+__device__ __forceinline__ f2 desing_pos2(const Par2& p, f2 h) {
+    const f2 rl = mk(__saturatef(p.kappa - h.x), __saturatef(p.kappa - h.y));
+    return fma2(mul(rl, rl), p.i2k, h);
 }
 
 // ---- one side of a pair of faces: physical flux, u+c and c-u with the dry gate folded into the inputs
@@ -123,8 +158,7 @@ __device__ __forceinline__ void side2(const Par2& p, f2 h, f2 hu, f2 hv, f2 F[3]
     const f2 pres = mul(p.K, hh);
     const f2 gh = mul(p.g, hm);
     const f2 c = mk(sqrt_a(gh.x), sqrt_a(gh.y));
-    const f2 t = fma2(hh, p.i2k, p.hk);
-    const f2 hs = mk(fmaxf(hm.x, fminf(t.x, p.kappa)), fmaxf(hm.y, fminf(t.y, p.kappa)));
+    const f2 hs = desing_pos2(p, hm);
     const f2 rm = mul(mk(rcp_a(hs.x), rcp_a(hs.y)), m);
     const f2 u = mul(hu, rm), v = mul(hv, rm);
     const f2 rh = mul(p.rho, hm);
@@ -145,15 +179,12 @@ __device__ __forceinline__ void side2(const Par2& p, f2 h, f2 hu, f2 hv, f2 F[3]
 }
 
 // ---- Kurganov-Petrova central-upwind flux through a pair of faces (centralupwind.jl:48-77) -------------
-// A warp whose faces are all dry on both sides skips the evaluation (all 32 lanes must be converged).
+// (The caller skips the evaluation for a warp whose faces are all dry on both sides.)
+__device__ __forceinline__ bool any_wet(const Par2& p, f2 hm, f2 hp) {
+    return fmaxf(fmaxf(hm.x, hm.y), fmaxf(hp.x, hp.y)) > p.cutoff;
+}
 template <int DIR, bool SPEED>
 __device__ __forceinline__ void cu2(const Par2& p, const f2 Um[3], const f2 Up[3], f2 F[3], f2& speed) {
-    const bool any = Um[0].x > p.cutoff || Um[0].y > p.cutoff || Up[0].x > p.cutoff || Up[0].y > p.cutoff;
-    if (!__any_sync(0xffffffffu, any)) {
-        F[0] = F[1] = F[2] = sp(0.0f);
-        speed = sp(0.0f);
-        return;
-    }
     f2 Fm[3], Fp[3], epm, enm, epp, enp;
     side2<DIR>(p, Um[0], Um[1], Um[2], Fm, epm, enm);
     side2<DIR>(p, Up[0], Up[1], Up[2], Fp, epp, enp);
@@ -175,44 +206,73 @@ __device__ __forceinline__ void cu2(const Par2& p, const f2 Um[3], const f2 Up[3
     else speed = sp(0.0f);
 }
 
-// ---- pointwise tail of a substep on a pair of cells: o = base + dt*d ; friction(prev) ; dry clean-up
-// (rungekutta.jl:39-41, friction.jl:62-84, timestepper.jl:41-51) --------------------------------------------
-__device__ __forceinline__ f2 friction_factor2(const Par2& p, const f2 prev[3], f2 Bc, f2 czdt) {
-    const f2 h = sub(prev[0], Bc);
-    const f2 t = fma2(mul(h, h), p.i2k, p.hk);
-    const f2 hs = mk(copysignf(fmaxf(fabsf(h.x), fminf(t.x, p.kappa)), h.x),
-                     copysignf(fmaxf(fabsf(h.y), fminf(t.y, p.kappa)), h.y));
-    const f2 r = mk(rcp_a(hs.x), rcp_a(hs.y));
-    const f2 u = mul(prev[1], r), v = mul(prev[2], r);
-    const f2 s2 = fma2(u, u, mul(v, v));
-    const f2 s = mk(sqrt_a(s2.x), sqrt_a(s2.y));
-    f2 iden;   // 1 / (law denominator)
-    if (p.friction == SWE_B200_FRICTION_BH2021) iden = mul(r, r);
-    else {
-        const f2 rc = mk(rcp_a(cbrt_a(hs.x)), rcp_a(cbrt_a(hs.y)));
-        iden = mul(rc, r);
-        if (p.friction != SWE_B200_FRICTION_BSA2012) iden = mul(iden, r);
+// ---- pointwise tail of a substep on a pair of cells (rungekutta.jl:39-41, friction.jl:62-84,
+// timestepper.jl:41-51): returns the factor the momenta are multiplied by -- 1/(1 - dt*c) of the implicit
+// friction times the wet flag of the dry clean-up -- and raises o0 to the cell bathymetry (for a wet cell
+// o0 - Bc >= cutoff >= 0, so the max is the identity there).
+template <int FRIC>
+__device__ __forceinline__ f2 tail_factor2(const Par2& p, const f2 prev[3], f2 Bc, f2 czdt, f2& o0) {
+    const f2 dpt = sub(o0, Bc);
+    f2 fac = mk(dpt.x < p.cutoff ? 0.0f : 1.0f, dpt.y < p.cutoff ? 0.0f : 1.0f);
+    o0 = mk(fmaxf(o0.x, Bc.x), fmaxf(o0.y, Bc.y));
+    if (FRIC != 0) {
+        const f2 h = sub(prev[0], Bc);
+        const f2 ha = mk(fabsf(h.x), fabsf(h.y));
+        const f2 hsa = desing_pos2(p, ha);                       // |h*|; h* = copysign(|h*|, h)
+        const f2 ra = mk(rcp_a(hsa.x), rcp_a(hsa.y));            // 1/|h*|
+        // speed = sqrt(u^2+v^2) = sqrt(hu^2+hv^2)/|h*|
+        const f2 m2 = fma2(prev[1], prev[1], mul(prev[2], prev[2]));
+        const f2 s = mul(mk(sqrt_a(m2.x), sqrt_a(m2.y)), ra);
+        f2 iden;                                                  // 1 / (law denominator), positive for every law
+        if (FRIC == 1) iden = mul(ra, ra);                       // h*^2              (friction_bh2021)
+        else {
+            const f2 rc = mk(rcp_a(cbrt_a(hsa.x)), rcp_a(cbrt_a(hsa.y)));
+            iden = mul(rc, ra);                                  // cbrt(h*) h*       (friction_bsa2012)
+            if (p.friction != SWE_B200_FRICTION_BSA2012) iden = mul(iden, ra);   // cbrt(h*) h*^2 (friction_fcg2016)
+        }
+        const f2 den = fma2(mul(s, iden), czdt, sp(1.0f));       // 1 - dt*(-Cz*speed/denominator)
+        fac = mul(fac, mk(rcp_a(den.x), rcp_a(den.y)));
     }
-    const f2 den = fma2(mul(s, iden), czdt, sp(1.0f));     // 1 - dt*(-Cz*speed/denominator)
-    return mk(rcp_a(den.x), rcp_a(den.y));
-}
-__device__ __forceinline__ void postproc2(const Par2& p, f2 o[3], f2 Bc) {
-    const f2 dpt = sub(o[0], Bc);
-    if (dpt.x < p.cutoff) { o[0].x = fmaxf(o[0].x, Bc.x); o[1].x = 0.0f; o[2].x = 0.0f; }
-    if (dpt.y < p.cutoff) { o[0].y = fmaxf(o[0].y, Bc.y); o[1].y = 0.0f; o[2].y = 0.0f; }
+    return fac;
 }
 
-struct CornerRow {
-    f2 e;       // corners (i, r), (i+1, r)
-    float e2;   // corner (i+2, r)
-    f2 ty;      // 2 * B_face_y of the two cells above this corner row
+// ---- asynchronous global -> shared copies (LDGSTS): a prefetched row costs no registers while in flight ----
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int NT = WPB * 32;
+
+// Per-thread rings in shared memory.  Every thread only ever reads what it copied itself (its own two
+// columns), so cp.async.wait_group is the only synchronisation: there is no barrier in the kernel.
+// The march is unrolled by 3 (the period of the 3-row register window), so a ring of depth 3 has compile-time
+// slots; depth-6 rings are 2 banks x 3 slots and the bank flips once per unrolled body.
+//   U : U^n rows.  Stage 2 reads row j again for the Heun average while row j+3 is in flight -> depth 6.
+//   D : dU rows (stage 2): row j+2 is consumed on arrival, row j+3 in flight            -> depth 3.
+//   E : bathymetry corner rows: j+1 (x faces), j+3 (arrived), j+4 (in flight)           -> depth 6.
+template <int STAGE>
+struct Rings {
+    f2 U[STAGE == 2 ? 2 : 1][3][3][NT];      // [bank][slot][variable][thread]
+    f2 D[STAGE == 2 ? 3 : 1][3][STAGE == 2 ? NT : 1];
+    f2 E[2][3][NT];
+    float E2[2][3][NT];
 };
 
-template <int RECON, bool HASB, int STAGE>
-__global__ void __launch_bounds__(WPB * 32, 4) k_stage_x2(const Args2 a) {
+template <int RECON, bool HASB, int STAGE, int FRIC, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
+    __shared__ Rings<STAGE> sm;
+    constexpr int UB = STAGE == 2 ? 2 : 1;               // banks of the U ring
     const Par2& p = a.p;
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * WPB + (threadIdx.x >> 5);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int tile = blockIdx.x * WPB + (tid >> 5);
     const int Nx = p.Nx, Ny = p.Ny;
     if (tile * VW + 2 >= Nx - 2) return;                 // warp-uniform: no output column
     const int i = tile * VW + 2 * lane;                  // first of this lane's two columns (even)
@@ -225,10 +285,12 @@ __global__ void __launch_bounds__(WPB * 32, 4) k_stage_x2(const Args2 a) {
     const bool faceb_ok = lane <= 30 && in_x;            // face (i+1 | i+2)
     const long long plane = p.plane;
     const int Bp = p.Bp;
+    // does this warp hold x-ghost pairs (columns 0,1 or Nx-2,Nx-1)?  warp-uniform
+    const bool ghost_warp = STAGE == 2 && (tile == 0 || tile * VW + 64 > Nx - 2);
 
     f2 dt = sp(0.0f), czdt = sp(0.0f);
     int xs = ic;
-    bool xswap = false, xflip = false;
+    bool xswap = false;
     if (STAGE == 2) {
         const float dts = (float)a.ctl->dt_s;
         dt = sp(dts);
@@ -236,54 +298,31 @@ __global__ void __launch_bounds__(WPB * 32, 4) k_stage_x2(const Args2 a) {
         if (ic < 2 || ic >= Nx - 2) {                    // a pair of x ghosts: where the BC copies them from
             const bool lo = ic < 2;
             if (p.bc == SWE_B200_BC_PERIODIC) xs = lo ? Nx - 4 : 2;
-            else { xs = lo ? 2 : Nx - 4; xswap = true; xflip = true; }
+            else { xs = lo ? 2 : Nx - 4; xswap = true; }   // wall: mirrored pair, normal momentum flips
         }
     }
-    const float rain = (float)a.ctl->rain;
-    const float infil_t = (float)a.ctl->infil;
+    // per-cell sources (system.jl:71-73): rain - infiltration is one constant per step unless a Horton factor plane exists
+    const float rain = p.rain_kind != SWE_B200_RAIN_NONE ? (float)a.ctl->rain : 0.0f;
+    const float infil_t = p.infil_kind != SWE_B200_INFIL_NONE ? (float)a.ctl->infil : 0.0f;
+    const f2 src = sp(a.factor ? rain : rain - infil_t);
+    const f2 ninfil = sp(-infil_t);
 
-    auto load_corner = [&](int row, CornerRow& c) {
-        if (HASB) {
-            const float* r = a.B + (size_t)row * Bp + ic;
-            c.e = *reinterpret_cast<const f2*>(r);
-            c.e2 = r[2];
-        }
+    struct Corner { f2 e; float e2; };                   // B[ic..ic+2, row]
+    auto ty_of = [&](const Corner& c) -> f2 {            // 2 * B_face_y of the two cells above that corner row
+        return HASB ? mk(c.e.x + c.e.y, c.e.y + c.e2) : sp(2.0f * p.constB);
     };
-    auto finish_corner = [&](CornerRow& c) {
-        if (HASB) c.ty = mk(c.e.x + c.e.y, c.e.y + c.e2);
-        else c.ty = sp(2.0f * p.constB);
-    };
-    auto bcell = [&](const CornerRow& lo, const CornerRow& hi) -> f2 {
-        return HASB ? mul(p.quarter, add(lo.ty, hi.ty)) : sp(p.constB);
-    };
-
-    // raw global loads of row j (U^n, and dU in stage 2), at the BC source position in stage 2
-    auto issue_row = [&](int j, f2 u[3], f2 d[3]) {
-        if (STAGE == 1) {
-            const float* s = a.U + (size_t)j * Nx + ic;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) u[k] = *reinterpret_cast<const f2*>(s + k * plane);
-        } else {
-            bool yflip;
-            const int ys = bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
-            const size_t off = (size_t)ys * Nx + xs;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                u[k] = *reinterpret_cast<const f2*>(a.U + off + k * plane);
-                d[k] = *reinterpret_cast<const f2*>(a.D + off + k * plane);
-            }
-        }
+    auto bcell = [&](f2 tylo, f2 tyhi) -> f2 { return HASB ? mul(p.quarter, add(tylo, tyhi)) : sp(p.constB); };
+    auto row_source = [&](int j, bool& yflip) -> int {   // stage 2: the row the y BC copies row j from
+        yflip = false;
+        if (STAGE == 1) return j;
+        return bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
     };
     // stage 1: q = U^n ; stage 2: q = U^1 = BC(postproc(friction(U^n + dt*dU))) rebuilt on the fly
-    auto finish_row = [&](int j, const f2 u[3], const f2 d[3], f2 Bc_here, f2 q[3], f2 un[3]) {
+    auto finish_row = [&](int j, int ys, bool yflip, const f2 u[3], const f2 d[3], f2 Bc_here, f2 q[3]) {
         if (STAGE == 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) q[k] = u[k];
         } else {
-            bool yflip;
-            const int ys = bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) un[k] = u[k];
             f2 Bm = Bc_here;
             if (HASB && (xs != ic || ys != j)) {         // ghost: bathymetry of the source cells
                 const float* r0 = a.B + (size_t)ys * Bp + xs;
@@ -292,175 +331,223 @@ __global__ void __launch_bounds__(WPB * 32, 4) k_stage_x2(const Args2 a) {
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) q[k] = fma2(dt, d[k], u[k]);
-            if (p.friction != SWE_B200_FRICTION_NONE) {
-                const f2 fr = friction_factor2(p, u, Bm, czdt);
-                q[1] = mul(q[1], fr);
-                q[2] = mul(q[2], fr);
-            }
-            postproc2(p, q, Bm);
-            if (xswap) {
+            const f2 fac = tail_factor2<FRIC>(p, u, Bm, czdt, q[0]);
+            q[1] = mul(q[1], fac);
+            q[2] = mul(q[2], fac);
+            if (ghost_warp && xswap) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) q[k] = swp(q[k]);
+                q[1] = neg(q[1]);
             }
-            if (xflip) q[1] = neg(q[1]);
             if (yflip) q[2] = neg(q[2]);
         }
     };
 
-    // ---- prologue: state rows ja-2 .. ja+1, corner rows ja-2 .. ja+2 ----
-    f2 q0[3], q1[3], q2[3], dprev[3];
-    f2 un0[3], un1[3], un2[3];
-    f2 Ry0[3], Gl[3], hsy;                                // upper face values / lower flux / (hL+hR) of cell j
+    // ---- prologue: state rows ja-2 .. ja+1 and corner rows ja-2 .. ja+2 by direct loads ----
+    f2 q[3][3];                                           // q[(j - ja) % 3] = row j of the (rebuilt) state
+    f2 dprev[3], Ry0[3], Gl[3], hsy;                      // y state of cell j: q(j+1)-q(j), upper face values, lower flux, hL+hR
+    Corner Ej;                                            // corner row j
+    f2 tyj, ty2;                                          // 2*B_face_y above corner rows j and j+2
     f2 msx = sp(0.0f), msy = sp(0.0f);
-    CornerRow cr[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { cr[r].e = sp(0.0f); cr[r].e2 = 0.0f; cr[r].ty = sp(0.0f); }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) un0[k] = un1[k] = un2[k] = sp(0.0f);
     {
-        CornerRow c0, c1, c2, c3, c4;                     // corner rows ja-2 .. ja+2
-        load_corner(ja - 2, c0); load_corner(ja - 1, c1); load_corner(ja, c2); load_corner(ja + 1, c3);
-        load_corner(ja + 2, c4);
+        Corner c[5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            c[r].e = sp(0.0f); c[r].e2 = 0.0f;
+            if (HASB) {
+                const float* g = a.B + (size_t)(ja - 2 + r) * Bp + ic;
+                c[r].e = *reinterpret_cast<const f2*>(g);
+                c[r].e2 = g[2];
+            }
+        }
         f2 u[4][3], d[4][3];
+        int ys[4];
+        bool yf[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
+            ys[r] = row_source(ja - 2 + r, yf[r]);
+            const size_t off = (size_t)ys[r] * Nx + xs;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) d[r][k] = sp(0.0f);
-            issue_row(ja - 2 + r, u[r], d[r]);
+            for (int k = 0; k < 3; ++k) {
+                u[r][k] = *reinterpret_cast<const f2*>(a.U + off + k * plane);
+                d[r][k] = STAGE == 2 ? *reinterpret_cast<const f2*>(a.D + off + k * plane) : sp(0.0f);
+            }
         }
-        finish_corner(c0); finish_corner(c1); finish_corner(c2); finish_corner(c3); finish_corner(c4);
-        f2 qa[3], qb[3], unx[3];
-        finish_row(ja - 2, u[0], d[0], bcell(c0, c1), qa, unx);
-        finish_row(ja - 1, u[1], d[1], bcell(c1, c2), qb, unx);
-        finish_row(ja, u[2], d[2], bcell(c2, c3), q0, un0);
-        finish_row(ja + 1, u[3], d[3], bcell(c3, c4), q1, un1);
+        if (STAGE == 2) {                                 // rows ja, ja+1 of U^n are read again by the Heun average
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sm.U[0][0][k][tid] = u[2][k]; sm.U[0][1][k][tid] = u[3][k]; }
+        }
+        if (HASB) {                                       // corner rows ja+1, ja+2 are read again for the x faces
+            sm.E[0][1][tid] = c[3].e; sm.E2[0][1][tid] = c[3].e2;
+            sm.E[0][2][tid] = c[4].e; sm.E2[0][2][tid] = c[4].e2;
+        }
+        const f2 tm2 = ty_of(c[0]), tm1 = ty_of(c[1]), t0 = ty_of(c[2]), t1 = ty_of(c[3]), t2 = ty_of(c[4]);
+        f2 qa[3], qb[3];
+        finish_row(ja - 2, ys[0], yf[0], u[0], d[0], bcell(tm2, tm1), qa);
+        finish_row(ja - 1, ys[1], yf[1], u[1], d[1], bcell(tm1, t0), qb);
+        finish_row(ja, ys[2], yf[2], u[2], d[2], bcell(t0, t1), q[0]);
+        finish_row(ja + 1, ys[3], yf[3], u[3], d[3], bcell(t1, t2), q[1]);
         f2 b0[3], b1[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { b0[k] = sub(qb[k], qa[k]); b1[k] = sub(q0[k], qb[k]); dprev[k] = sub(q1[k], q0[k]); }
+        for (int k = 0; k < 3; ++k) {
+            b0[k] = sub(qb[k], qa[k]); b1[k] = sub(q[0][k], qb[k]); dprev[k] = sub(q[1][k], q[0][k]);
+        }
         f2 Lt[3], Rp[3], Ly0[3];
-        recon2<RECON>(p, qb, b0, b1, c1.ty, c2.ty, bcell(c1, c2), Lt, Rp);          // cell ja-1: upper face only
-        recon2<RECON>(p, q0, b1, dprev, c2.ty, c3.ty, bcell(c2, c3), Ly0, Ry0);     // cell ja
-        f2 s;
-        cu2<1, STAGE == 1>(p, Rp, Ly0, Gl, s);                                      // face ja-1/2
+        recon2<RECON>(p, qb, b0, b1, tm1, t0, bcell(tm1, t0), Lt, Rp);              // cell ja-1: upper face only
+        recon2<RECON>(p, q[0], b1, dprev, t0, t1, bcell(t0, t1), Ly0, Ry0);         // cell ja
+        f2 s = sp(0.0f);
+        Gl[0] = Gl[1] = Gl[2] = sp(0.0f);
+        if (__any_sync(0xffffffffu, any_wet(p, Rp[0], Ly0[0]))) cu2<1, STAGE == 1>(p, Rp, Ly0, Gl, s);   // face ja-1/2
         if (STAGE == 1 && out_pair) msy = s;
         hsy = add(Ly0[0], Ry0[0]);
-        cr[0] = c2; cr[1] = c3; cr[2] = c4;               // corner rows ja, ja+1, ja+2
+        Ej = c[2];
+        tyj = t0;
+        ty2 = t2;
     }
 
-    // ---- march ----
-    f2 ru[3], rd[3];
-    CornerRow pc;
+    // ---- fetch of state row r / corner row r into the rings (slot, bank given by the caller) ----
+    int ys_next;                                          // BC source row of the state row in flight
+    bool yflip_next;
+    auto fetch_row = [&](int row, int bank, int slot) {
+        const int rr = min(row, Ny - 1);
+        ys_next = row_source(rr, yflip_next);
+        const size_t off = (size_t)ys_next * Nx + xs;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) rd[k] = sp(0.0f);
-    pc.e = sp(0.0f); pc.e2 = 0.0f; pc.ty = sp(0.0f);
-    issue_row(min(ja + 2, Ny - 1), ru, rd);
-    load_corner(min(ja + 3, Ny), pc);
-#pragma unroll 2
-    for (int j = ja; j < jb; ++j) {
-        // window: q0 = row j, q1 = row j+1 ; corner rows cr[0..3] = j .. j+3
-        cr[3] = pc;
-        finish_corner(cr[3]);
-        finish_row(j + 2, ru, rd, bcell(cr[2], cr[3]), q2, un2);
-        issue_row(min(j + 3, Ny - 1), ru, rd);            // in flight during this row's arithmetic
-        load_corner(min(j + 4, Ny), pc);
-
-        f2 dU[3];
-        // ================= x direction (row j) =================
-        {
-            f2 bwd[3], fwd[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float ql = __shfl_up_sync(0xffffffffu, q0[k].y, 1);      // column i-1
-                const float qr = __shfl_down_sync(0xffffffffu, q0[k].x, 1);    // column i+2
-                const float dm = q0[k].y - q0[k].x;
-                bwd[k] = mk(q0[k].x - ql, dm);
-                fwd[k] = mk(dm, qr - q0[k].y);
-            }
-            f2 tBl, tBr;
-            if (HASB) {
-                tBl = add(cr[0].e, cr[1].e);
-                tBr = mk(tBl.y, cr[0].e2 + cr[1].e2);
-            } else tBl = tBr = sp(2.0f * p.constB);
-            f2 Lx[3], Rx[3], Ln[3];
-            recon2<RECON>(p, q0, bwd, fwd, tBl, tBr, bcell(cr[0], cr[1]), Lx, Rx);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) Ln[k] = mk(Lx[k].y, __shfl_down_sync(0xffffffffu, Lx[k].x, 1));
-            f2 F[3], s;
-            cu2<0, STAGE == 1>(p, Rx, Ln, F, s);           // faces (i | i+1) and (i+1 | i+2)
-            if (STAGE == 1) {
-                if (facea_ok) msx.x = fmaxf(msx.x, s.x);
-                if (faceb_ok) msx.y = fmaxf(msx.y, s.y);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const f2 Fl = mk(__shfl_up_sync(0xffffffffu, F[k].y, 1), F[k].x);
-                dU[k] = mul(p.nrdx, sub(F[k], Fl));
-            }
-            if (HASB && p.bottom_source) dU[1] = fma2(mul(p.botx, sub(tBr, tBl)), add(Lx[0], Rx[0]), dU[1]);
+        for (int k = 0; k < 3; ++k) {
+            cp_async8(&sm.U[bank][slot][k][tid], a.U + off + k * plane);
+            if (STAGE == 2) cp_async8(&sm.D[slot][k][tid], a.D + off + k * plane);
         }
-        // ================= y direction (cell j, faces j-1/2 and j+1/2) =================
-        {
-            f2 fwd[3], Ly1[3], Ry1[3];
+    };
+    auto fetch_corner = [&](int row, int bank, int slot) {
+        if (HASB) {
+            const float* g = a.B + (size_t)min(row, Ny) * Bp + ic;
+            cp_async8(&sm.E[bank][slot][tid], g);
+            cp_async4(&sm.E2[bank][slot][tid], g + 2);
+        }
+    };
+    fetch_row(ja + 2, 0, 2);
+    fetch_corner(ja + 3, 1, 0);
+    cp_async_commit();
+
+    // ---- march: 3 rows per trip; rows beyond jb (last chunk only) are computed on clamped data and not stored ----
+    int bank = 0;                                         // (j0 - ja) / 3 mod 2
+    for (int j0 = ja; j0 < jb; j0 += 3, bank ^= 1) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) fwd[k] = sub(q2[k], q1[k]);
-            recon2<RECON>(p, q1, dprev, fwd, cr[1].ty, cr[2].ty, bcell(cr[1], cr[2]), Ly1, Ry1);   // cell j+1
-            f2 G[3], s;
-            cu2<1, STAGE == 1>(p, Ry0, Ly1, G, s);         // face j+1/2
-            if (STAGE == 1 && out_pair) { msy.x = fmaxf(msy.x, s.x); msy.y = fmaxf(msy.y, s.y); }
+        for (int R = 0; R < 3; ++R) {
+            const int j = j0 + R;
+            f2* q0 = q[R];
+            f2* q1 = q[(R + 1) % 3];
+            f2* q2 = q[(R + 2) % 3];
+            // ---- arrivals: state row j+2 and corner row j+3 ----
+            cp_async_wait_all();
+            const int ys2 = ys_next;
+            const bool yflip2 = yflip_next;
+            f2 ru[3], rd[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) dU[k] = fma2(p.nrdy, sub(G[k], Gl[k]), dU[k]);
-            if (HASB && p.bottom_source) dU[2] = fma2(mul(p.boty, sub(cr[1].ty, cr[0].ty)), hsy, dU[2]);
+            for (int k = 0; k < 3; ++k) {
+                ru[k] = sm.U[(bank + (R + 2) / 3) % UB][(R + 2) % 3][k][tid];
+                rd[k] = STAGE == 2 ? sm.D[(R + 2) % 3][k][tid] : sp(0.0f);
+            }
+            Corner E1, E3;                                // corner rows j+1 and j+3
+            E1.e = sp(0.0f); E1.e2 = 0.0f; E3 = E1;
+            if (HASB) {
+                E1.e = sm.E[(bank + (R + 1) / 3) & 1][(R + 1) % 3][tid];
+                E1.e2 = sm.E2[(bank + (R + 1) / 3) & 1][(R + 1) % 3][tid];
+                E3.e = sm.E[(bank + 1) & 1][R][tid];
+                E3.e2 = sm.E2[(bank + 1) & 1][R][tid];
+            }
+            fetch_row(j + 3, (bank + 1) % UB, R);          // in flight during this row's arithmetic
+            fetch_corner(j + 4, (bank + (R + 4) / 3) & 1, (R + 1) % 3);
+            cp_async_commit();
+            const f2 ty1 = ty_of(E1), ty3 = ty_of(E3);
+            finish_row(j + 2, ys2, yflip2, ru, rd, bcell(ty2, ty3), q2);
+
+            // ================= reconstruction: row j in x, cell j+1 in y =================
+            f2 Lx[3], Rx[3], Ln[3], tBl, tBr, fwd[3], Ly1[3], Ry1[3];
+            {
+                float ql[3], qr[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    ql[k] = __shfl_up_sync(0xffffffffu, q0[k].y, 1);      // column i-1
+                    qr[k] = __shfl_down_sync(0xffffffffu, q0[k].x, 1);    // column i+2
+                }
+                if (HASB) {
+                    tBl = add(Ej.e, E1.e);
+                    tBr = mk(tBl.y, Ej.e2 + E1.e2);
+                } else tBl = tBr = sp(2.0f * p.constB);
+                recon2x<RECON>(p, q0, ql, qr, tBl, tBr, bcell(tyj, ty1), Lx, Rx);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Ln[k] = mk(Lx[k].y, __shfl_down_sync(0xffffffffu, Lx[k].x, 1));
+#pragma unroll
+                for (int k = 0; k < 3; ++k) fwd[k] = sub(q2[k], q1[k]);
+                recon2<RECON>(p, q1, dprev, fwd, ty1, ty2, bcell(ty1, ty2), Ly1, Ry1);   // cell j+1
+            }
+            // ================= fluxes: faces (i|i+1), (i+1|i+2) of row j and face j+1/2 =================
+            // one warp-uniform decision per row: a warp whose x and y faces are all dry skips both evaluations
+            f2 F[3], G[3];
+            const bool wet = any_wet(p, Rx[0], Ln[0]) || any_wet(p, Ry0[0], Ly1[0]);
+            if (__any_sync(0xffffffffu, wet)) {
+                f2 sx, sy;
+                cu2<0, STAGE == 1>(p, Rx, Ln, F, sx);
+                cu2<1, STAGE == 1>(p, Ry0, Ly1, G, sy);
+                if (STAGE == 1 && j < jb) {
+                    if (facea_ok) msx.x = fmaxf(msx.x, sx.x);
+                    if (faceb_ok) msx.y = fmaxf(msx.y, sx.y);
+                    if (out_pair) { msy.x = fmaxf(msy.x, sy.x); msy.y = fmaxf(msy.y, sy.y); }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) F[k] = G[k] = sp(0.0f);
+            }
+            // ================= flux differences, bottom-slope source, per-cell sources =================
+            f2 dU[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float Fp = __shfl_up_sync(0xffffffffu, F[k].y, 1);          // face (i-1 | i)
+                const f2 dF = mk(F[k].x - Fp, F[k].y - F[k].x);
+                dU[k] = fma2(p.nrdy, sub(G[k], Gl[k]), mul(p.nrdx, dF));
+            }
+            if (HASB) {
+                dU[1] = fma2(mul(p.botx, sub(tBr, tBl)), add(Lx[0], Rx[0]), dU[1]);
+                dU[2] = fma2(mul(p.boty, sub(ty1, tyj)), hsy, dU[2]);
+            }
+            dU[0] = add(dU[0], src);
+            if (a.factor) {
+                const double2 fc = *reinterpret_cast<const double2*>(a.factor + (size_t)min(j, Ny - 1) * Nx + ic);
+                dU[0] = fma2(mk((float)fc.x, (float)fc.y), ninfil, dU[0]);
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) { dprev[k] = fwd[k]; Ry0[k] = Ry1[k]; Gl[k] = G[k]; }
             hsy = add(Ly1[0], Ry1[0]);
-        }
-        // ================= per-cell sources (system.jl:71-73, list order) =================
+            // ================= store =================
+            const bool st = out_pair && j < jb;
+            if (STAGE == 1) {
+                if (st) {
+                    float* o = a.out + (size_t)j * Nx + i;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const bool do_infil = (pass == 0) == (p.infil_first != 0);
-            if (do_infil && p.infil_kind != SWE_B200_INFIL_NONE) {
-                f2 f;
-                if (a.factor) {
-                    const double2 fc = *reinterpret_cast<const double2*>(a.factor + (size_t)j * Nx + ic);
-                    f = mul(mk((float)fc.x, (float)fc.y), sp(infil_t));
-                } else f = sp(infil_t);
-                dU[0] = sub(dU[0], f);
+                    for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(o + k * plane) = dU[k];
+                }
+            } else {
+                // rungekutta.jl:39-49 stage 2, then friction (prev = U^1) and the dry clean-up
+                f2 o[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) o[k] = mul(p.half, add(sm.U[bank % UB][R][k][tid], fma2(dt, dU[k], q0[k])));
+                const f2 fac = tail_factor2<FRIC>(p, q0, bcell(tyj, ty1), czdt, o[0]);
+                o[1] = mul(o[1], fac);
+                o[2] = mul(o[2], fac);
+                if (st) {
+                    float* w = a.out + (size_t)j * Nx + i;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(w + k * plane) = o[k];
+                }
             }
-            if (!do_infil && p.rain_kind != SWE_B200_RAIN_NONE) dU[0] = add(dU[0], sp(rain));
+            // corner state of the next row
+            Ej = E1;
+            tyj = ty1;
+            ty2 = ty3;
         }
-        // ================= store =================
-        if (STAGE == 1) {
-            if (out_pair) {
-                float* o = a.out + (size_t)j * Nx + i;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(o + k * plane) = dU[k];
-            }
-        } else {
-            // rungekutta.jl:39-49 stage 2, then friction (prev = U^1) and the dry clean-up
-            f2 o[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) o[k] = mul(p.half, add(un0[k], fma2(dt, dU[k], q0[k])));
-            const f2 Bm = bcell(cr[0], cr[1]);
-            if (p.friction != SWE_B200_FRICTION_NONE) {
-                const f2 fr = friction_factor2(p, q0, Bm, czdt);
-                o[1] = mul(o[1], fr);
-                o[2] = mul(o[2], fr);
-            }
-            postproc2(p, o, Bm);
-            if (out_pair) {
-                float* w = a.out + (size_t)j * Nx + i;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(w + k * plane) = o[k];
-            }
-        }
-        // ================= rotate =================
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            q0[k] = q1[k]; q1[k] = q2[k];
-            un0[k] = un1[k]; un1[k] = un2[k];
-        }
-        cr[0] = cr[1]; cr[1] = cr[2]; cr[2] = cr[3];
     }
+    cp_async_wait_all();
 
     if (STAGE == 1) {
         // CFL reduction: warp shuffle -> one atomicMax per warp and direction (non-negative bit patterns)
