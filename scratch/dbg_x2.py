@@ -24,3 +24,12 @@ for n in range(1, 101):
             for k in range(3):
                 d = np.abs(A[k].astype(np.float64) - O[k]); idx = np.unravel_index(np.argmax(d), d.shape)
                 print("   worst cell var", k, idx, "x2", A[k][idx], "oracle", O[k][idx], "generic", B[k][idx])
+# error map after a single step from the initial state
+a2, o2 = mk(False), oracle.OracleSim(case)
+o2.set_state_interior(*state); a2.step(mts); o2.step(mts)
+A, O = a2.get_state_full(), o2.get_state_full()
+d = np.max(np.abs(A.astype(np.float64) - O), axis=0)
+bad = d > 1e-5 * max(1.0, np.max(np.abs(O)))
+print("full array shape", A.shape, "bad cells", int(bad.sum()))
+rows = np.where(bad.any(axis=1))[0]; cols = np.where(bad.any(axis=0))[0]
+print("bad rows (axis1 idx):", rows[:40], "...", len(rows)); print("bad cols (axis2 idx):", cols[:40], "...", len(cols))

@@ -184,13 +184,17 @@ public:
         q.g = s2(c.g); q.K = s2(0.5 * c.rho * c.g); q.i2k = s2(1.0 / (2 * c.kappa)); q.hk = s2(c.kappa / 2.0);
         q.rho = s2(c.rho); q.nrdx = s2(-1.0 / dx); q.nrdy = s2(-1.0 / dy);
         q.botx = s2(c.has_bottom_source ? -0.25 * c.g / dx : 0.0); q.boty = s2(c.has_bottom_source ? -0.25 * c.g / dy : 0.0); q.Cz = s2(c.Cz);
+        {   // rows per block: a multiple of 3 (the march is unrolled by 3), long chunks on large grids (the 4-row
+            // prologue amortises), but at least ~2 waves of 4 blocks per SM on small ones
+            const int ntiles = (c.nx + x2::VW - 1) / x2::VW, bx = (ntiles + x2::WPB - 1) / x2::WPB;
+            const int want_by = (148 * 4 * 2 + bx - 1) / bx;
+            q.rows = std::min(126, std::max(12, c.ny / std::max(1, want_by) / 3 * 3));
+        }
         if (const char* e = std::getenv("SWE_B200_X2_ROWS")) q.rows = std::max(3, atoi(e) / 3 * 3);   // multiple of 3
-        if (const char* e = std::getenv("SWE_B200_X2_MINB")) x2_minb = atoi(e);
         x2_ok = true;
     }
-    int x2_minb = 4;        // resident blocks per SM the x2 kernels are compiled for (register cap 96 / 128)
-    template <int STAGE, int MINB>
-    void launch_stage_x2_m(const S* U, const S* D, S* out) {
+    template <int STAGE>
+    void launch_stage_x2(const S* U, const S* D, S* out) {
         if constexpr (std::is_same<P, Policy<float, float, false>>::value) {
             x2::Args2 a;
             a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl;
@@ -199,12 +203,17 @@ public:
             dim3 b(x2::WPB * 32);
             const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
             const int fr = cfg.friction == SWE_B200_FRICTION_NONE ? 0 : (cfg.friction == SWE_B200_FRICTION_BH2021 ? 1 : 2);
-#define SWE_X2_LAUNCH(R, HB, F) x2::k_stage_x2<R, HB, STAGE, (STAGE == 2 ? F : 0), MINB><<<g, b, 0, stream>>>(a)
+#define SWE_X2_LAUNCH(R, HB, F, FP) x2::k_stage_x2<R, HB, STAGE, (STAGE == 2 ? F : 0), FP><<<g, b, 0, stream>>>(a)
+#define SWE_X2_FACT(R, HB, F)                                                                \
+    do {                                                                                     \
+        if (factor) SWE_X2_LAUNCH(R, HB, F, true);                                           \
+        else SWE_X2_LAUNCH(R, HB, F, false);                                                 \
+    } while (0)
 #define SWE_X2_FRIC(R, HB)                                                                   \
     do {                                                                                     \
-        if (STAGE == 1 || fr == 0) SWE_X2_LAUNCH(R, HB, 0);                                  \
-        else if (fr == 1) SWE_X2_LAUNCH(R, HB, 1);                                           \
-        else SWE_X2_LAUNCH(R, HB, 2);                                                        \
+        if (STAGE == 1 || fr == 0) SWE_X2_FACT(R, HB, 0);                                    \
+        else if (fr == 1) SWE_X2_FACT(R, HB, 1);                                             \
+        else SWE_X2_FACT(R, HB, 2);                                                          \
     } while (0)
             if (B) {
                 if (lin) SWE_X2_FRIC(1, true);
@@ -214,13 +223,9 @@ public:
                 else SWE_X2_FRIC(0, false);
             }
 #undef SWE_X2_FRIC
+#undef SWE_X2_FACT
 #undef SWE_X2_LAUNCH
         }
-    }
-    template <int STAGE>
-    void launch_stage_x2(const S* U, const S* D, S* out) {
-        if (x2_minb == 4) launch_stage_x2_m<STAGE, 4>(U, D, out);
-        else launch_stage_x2_m<STAGE, 5>(U, D, out);
     }
 
     // ------------------------------------------------------------------------------------------

@@ -18,6 +18,9 @@
 // Semantics are those of kernels_fused.cuh (same reference citations); parity: tests/test_gpu_parity.py
 // compares this path against the CPU oracle at rel-Linf <= 1e-5 (the north_star Float32 tolerance).
 #pragma once
+#include <cstddef>
+#include <type_traits>
+
 #include "kernels_fused.cuh"
 
 namespace swe {
@@ -265,8 +268,8 @@ struct Rings {
     float E2[2][3][NT];
 };
 
-template <int RECON, bool HASB, int STAGE, int FRIC, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
+template <int RECON, bool HASB, int STAGE, int FRIC, bool FACTOR>
+__global__ void __launch_bounds__(NT, 4) k_stage_x2(const Args2 a) {
     __shared__ Rings<STAGE> sm;
     constexpr int UB = STAGE == 2 ? 2 : 1;               // banks of the U ring
     const Par2& p = a.p;
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
     // per-cell sources (system.jl:71-73): rain - infiltration is one constant per step unless a Horton factor plane exists
     const float rain = p.rain_kind != SWE_B200_RAIN_NONE ? (float)a.ctl->rain : 0.0f;
     const float infil_t = p.infil_kind != SWE_B200_INFIL_NONE ? (float)a.ctl->infil : 0.0f;
-    const f2 src = sp(a.factor ? rain : rain - infil_t);
+    const f2 src = sp(FACTOR ? rain : rain - infil_t);
     const f2 ninfil = sp(-infil_t);
 
     struct Corner { f2 e; float e2; };                   // B[ic..ic+2, row]
@@ -318,13 +321,14 @@ __global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
         return bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
     };
     // stage 1: q = U^n ; stage 2: q = U^1 = BC(postproc(friction(U^n + dt*dU))) rebuilt on the fly
-    auto finish_row = [&](int j, int ys, bool yflip, const f2 u[3], const f2 d[3], f2 Bc_here, f2 q[3]) {
+    const bool xghost = xs != ic;
+    auto finish_row = [&](bool remapped, int ys, bool yflip, const f2 u[3], const f2 d[3], f2 Bc_here, f2 q[3]) {
         if (STAGE == 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) q[k] = u[k];
         } else {
             f2 Bm = Bc_here;
-            if (HASB && (xs != ic || ys != j)) {         // ghost: bathymetry of the source cells
+            if (HASB && (xghost || remapped)) {          // ghost: bathymetry of the source cells
                 const float* r0 = a.B + (size_t)ys * Bp + xs;
                 const float m = r0[1] + r0[Bp + 1];
                 Bm = mk(0.25f * (r0[0] + r0[Bp] + m), 0.25f * (m + r0[2] + r0[Bp + 2]));
@@ -383,10 +387,10 @@ __global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
         }
         const f2 tm2 = ty_of(c[0]), tm1 = ty_of(c[1]), t0 = ty_of(c[2]), t1 = ty_of(c[3]), t2 = ty_of(c[4]);
         f2 qa[3], qb[3];
-        finish_row(ja - 2, ys[0], yf[0], u[0], d[0], bcell(tm2, tm1), qa);
-        finish_row(ja - 1, ys[1], yf[1], u[1], d[1], bcell(tm1, t0), qb);
-        finish_row(ja, ys[2], yf[2], u[2], d[2], bcell(t0, t1), q[0]);
-        finish_row(ja + 1, ys[3], yf[3], u[3], d[3], bcell(t1, t2), q[1]);
+        finish_row(ys[0] != ja - 2, ys[0], yf[0], u[0], d[0], bcell(tm2, tm1), qa);
+        finish_row(ys[1] != ja - 1, ys[1], yf[1], u[1], d[1], bcell(tm1, t0), qb);
+        finish_row(ys[2] != ja, ys[2], yf[2], u[2], d[2], bcell(t0, t1), q[0]);
+        finish_row(ys[3] != ja + 1, ys[3], yf[3], u[3], d[3], bcell(t1, t2), q[1]);
         f2 b0[3], b1[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -405,33 +409,70 @@ __global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
         ty2 = t2;
     }
 
-    // ---- fetch of state row r / corner row r into the rings (slot, bank given by the caller) ----
-    int ys_next;                                          // BC source row of the state row in flight
-    bool yflip_next;
-    auto fetch_row = [&](int row, int bank, int slot) {
-        const int rr = min(row, Ny - 1);
-        ys_next = row_source(rr, yflip_next);
-        const size_t off = (size_t)ys_next * Nx + xs;
+    // ---- fetch of state row r / corner row r into the rings ----
+    // Running byte pointers advance by one row per fetch.  A trip (3 rows) is FAST when every row it fetches is
+    // an interior row (no y-BC remap, no clamping, every row stored); only the last trip(s) of the last chunk
+    // take the generic path.
+    const long long rowB = (long long)Nx * 4, planeB = plane * 4;
+    const long long dOff = (const char*)a.D - (const char*)a.U;
+    const char* pf = (const char*)(a.U + (size_t)(ja + 2) * Nx + xs);     // next state row to fetch
+    const char* pc = (const char*)(a.B + (size_t)(ja + 3) * Bp + ic);     // next corner row to fetch
+    char* ps = (char*)(a.out + (size_t)ja * Nx + i);                      // row j of the output
+    const double* pfac = a.factor + (size_t)ja * Nx + ic;                 // Horton factor plane, row j
+    int ys_next = 0;                                      // BC source row of the state row in flight (generic path)
+    bool yflip_next = false, remap_next = false;
+    // ring addressing in bytes: this thread's 8-byte (4-byte for E2) column inside every [.. ][NT] row
+    char* const smb = reinterpret_cast<char*>(&sm);
+    constexpr unsigned U_BANK = 3 * 3 * NT * 8, U_SLOT = 3 * NT * 8, U_VAR = NT * 8;
+    constexpr unsigned D_OFF = offsetof(Rings<STAGE>, D), E_OFF = offsetof(Rings<STAGE>, E), E2_OFF = offsetof(Rings<STAGE>, E2);
+    constexpr unsigned E_BANK = 3 * NT * 8, E_SLOT = NT * 8, E2_BANK = 3 * NT * 4, E2_SLOT = NT * 4;
+    char* const smU = smb + tid * 8;
+    char* const smD = smb + D_OFF + tid * 8;
+    char* const smE = smb + E_OFF + tid * 8;
+    char* const smE2 = smb + E2_OFF + tid * 4;
+    auto fetch_row = [&](auto fast_tag, int row, unsigned ubank, int slot) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        const char* g = pf;
+        if (!FAST) {
+            remap_next = false;
+            yflip_next = false;
+            ys_next = row;
+            if (row >= Ny - 2) {                          // uniform
+                const int rr = min(row, Ny - 1);
+                ys_next = row_source(rr, yflip_next);
+                remap_next = ys_next != row;
+                g = (const char*)(a.U + (size_t)ys_next * Nx + xs);
+            }
+        }
+        pf += rowB;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            cp_async8(&sm.U[bank][slot][k][tid], a.U + off + k * plane);
-            if (STAGE == 2) cp_async8(&sm.D[slot][k][tid], a.D + off + k * plane);
+            cp_async8(smU + ubank + slot * U_SLOT + k * U_VAR, g + k * planeB);
+            if (STAGE == 2) cp_async8(smD + slot * U_SLOT + k * U_VAR, g + dOff + k * planeB);
         }
     };
-    auto fetch_corner = [&](int row, int bank, int slot) {
+    auto fetch_corner = [&](auto fast_tag, int row, unsigned ebank, unsigned e2bank, int slot) {
+        constexpr bool FAST = decltype(fast_tag)::value;
         if (HASB) {
-            const float* g = a.B + (size_t)min(row, Ny) * Bp + ic;
-            cp_async8(&sm.E[bank][slot][tid], g);
-            cp_async4(&sm.E2[bank][slot][tid], g + 2);
+            const char* g = pc;
+            if (!FAST && row > Ny) g = (const char*)(a.B + (size_t)Ny * Bp + ic);
+            pc += (long long)Bp * 4;
+            cp_async8(smE + ebank + slot * E_SLOT, g);
+            cp_async4(smE2 + e2bank + slot * E2_SLOT, g + 8);
         }
     };
-    fetch_row(ja + 2, 0, 2);
-    fetch_corner(ja + 3, 1, 0);
+    fetch_row(std::false_type{}, ja + 2, 0u, 2);
+    fetch_corner(std::false_type{}, ja + 3, E_BANK, E2_BANK, 0);
     cp_async_commit();
 
     // ---- march: 3 rows per trip; rows beyond jb (last chunk only) are computed on clamped data and not stored ----
     int bank = 0;                                         // (j0 - ja) / 3 mod 2
-    for (int j0 = ja; j0 < jb; j0 += 3, bank ^= 1) {
+    auto trip = [&](auto fast_tag, const int j0) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        // byte offsets of the bank holding rows j0.. (index 0) and of the other bank (index 1)
+        const unsigned uU[2] = {UB == 2 && bank ? U_BANK : 0u, UB == 2 && !bank ? U_BANK : 0u};
+        const unsigned uE[2] = {bank ? E_BANK : 0u, bank ? 0u : E_BANK};
+        const unsigned uE2[2] = {bank ? E2_BANK : 0u, bank ? 0u : E2_BANK};
 #pragma unroll
         for (int R = 0; R < 3; ++R) {
             const int j = j0 + R;
@@ -440,27 +481,28 @@ __global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
             f2* q2 = q[(R + 2) % 3];
             // ---- arrivals: state row j+2 and corner row j+3 ----
             cp_async_wait_all();
-            const int ys2 = ys_next;
-            const bool yflip2 = yflip_next;
+            // (a FAST trip does not maintain ys_next / the flags: rows it fetched are never remapped)
+            const bool yflip2 = !FAST && yflip_next, remap2 = !FAST && remap_next;
+            const int ys2 = remap2 ? ys_next : j + 2;
             f2 ru[3], rd[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                ru[k] = sm.U[(bank + (R + 2) / 3) % UB][(R + 2) % 3][k][tid];
-                rd[k] = STAGE == 2 ? sm.D[(R + 2) % 3][k][tid] : sp(0.0f);
+                ru[k] = *reinterpret_cast<const f2*>(smU + uU[((R + 2) / 3) & 1] + ((R + 2) % 3) * U_SLOT + k * U_VAR);
+                rd[k] = STAGE == 2 ? *reinterpret_cast<const f2*>(smD + ((R + 2) % 3) * U_SLOT + k * U_VAR) : sp(0.0f);
             }
             Corner E1, E3;                                // corner rows j+1 and j+3
             E1.e = sp(0.0f); E1.e2 = 0.0f; E3 = E1;
             if (HASB) {
-                E1.e = sm.E[(bank + (R + 1) / 3) & 1][(R + 1) % 3][tid];
-                E1.e2 = sm.E2[(bank + (R + 1) / 3) & 1][(R + 1) % 3][tid];
-                E3.e = sm.E[(bank + 1) & 1][R][tid];
-                E3.e2 = sm.E2[(bank + 1) & 1][R][tid];
+                E1.e = *reinterpret_cast<const f2*>(smE + uE[((R + 1) / 3) & 1] + ((R + 1) % 3) * E_SLOT);
+                E1.e2 = *reinterpret_cast<const float*>(smE2 + uE2[((R + 1) / 3) & 1] + ((R + 1) % 3) * E2_SLOT);
+                E3.e = *reinterpret_cast<const f2*>(smE + uE[1] + R * E_SLOT);
+                E3.e2 = *reinterpret_cast<const float*>(smE2 + uE2[1] + R * E2_SLOT);
             }
-            fetch_row(j + 3, (bank + 1) % UB, R);          // in flight during this row's arithmetic
-            fetch_corner(j + 4, (bank + (R + 4) / 3) & 1, (R + 1) % 3);
+            fetch_row(fast_tag, j + 3, uU[1], R);          // in flight during this row's arithmetic
+            fetch_corner(fast_tag, j + 4, uE[((R + 4) / 3) & 1], uE2[((R + 4) / 3) & 1], (R + 1) % 3);
             cp_async_commit();
             const f2 ty1 = ty_of(E1), ty3 = ty_of(E3);
-            finish_row(j + 2, ys2, yflip2, ru, rd, bcell(ty2, ty3), q2);
+            finish_row(remap2, ys2, yflip2, ru, rd, bcell(ty2, ty3), q2);
 
             // ================= reconstruction: row j in x, cell j+1 in y =================
             f2 Lx[3], Rx[3], Ln[3], tBl, tBr, fwd[3], Ly1[3], Ry1[3];
@@ -490,7 +532,7 @@ __global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
                 f2 sx, sy;
                 cu2<0, STAGE == 1>(p, Rx, Ln, F, sx);
                 cu2<1, STAGE == 1>(p, Ry0, Ly1, G, sy);
-                if (STAGE == 1 && j < jb) {
+                if (STAGE == 1 && (FAST || j < jb)) {
                     if (facea_ok) msx.x = fmaxf(msx.x, sx.x);
                     if (faceb_ok) msx.y = fmaxf(msx.y, sx.y);
                     if (out_pair) { msy.x = fmaxf(msy.x, sy.x); msy.y = fmaxf(msy.y, sy.y); }
@@ -512,40 +554,47 @@ __global__ void __launch_bounds__(NT, MINB) k_stage_x2(const Args2 a) {
                 dU[2] = fma2(mul(p.boty, sub(ty1, tyj)), hsy, dU[2]);
             }
             dU[0] = add(dU[0], src);
-            if (a.factor) {
-                const double2 fc = *reinterpret_cast<const double2*>(a.factor + (size_t)min(j, Ny - 1) * Nx + ic);
+            if (FACTOR) {
+                const double2 fc = *reinterpret_cast<const double2*>(FAST || j < Ny ? pfac : a.factor);
+                pfac += Nx;
                 dU[0] = fma2(mk((float)fc.x, (float)fc.y), ninfil, dU[0]);
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) { dprev[k] = fwd[k]; Ry0[k] = Ry1[k]; Gl[k] = G[k]; }
             hsy = add(Ly1[0], Ry1[0]);
             // ================= store =================
-            const bool st = out_pair && j < jb;
+            const bool st = out_pair && (FAST || j < jb);
             if (STAGE == 1) {
                 if (st) {
-                    float* o = a.out + (size_t)j * Nx + i;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(o + k * plane) = dU[k];
+                    for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(ps + k * planeB) = dU[k];
                 }
             } else {
                 // rungekutta.jl:39-49 stage 2, then friction (prev = U^1) and the dry clean-up
                 f2 o[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) o[k] = mul(p.half, add(sm.U[bank % UB][R][k][tid], fma2(dt, dU[k], q0[k])));
+                for (int k = 0; k < 3; ++k) {
+                    const f2 un = *reinterpret_cast<const f2*>(smU + uU[0] + R * U_SLOT + k * U_VAR);
+                    o[k] = mul(p.half, add(un, fma2(dt, dU[k], q0[k])));
+                }
                 const f2 fac = tail_factor2<FRIC>(p, q0, bcell(tyj, ty1), czdt, o[0]);
                 o[1] = mul(o[1], fac);
                 o[2] = mul(o[2], fac);
                 if (st) {
-                    float* w = a.out + (size_t)j * Nx + i;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(w + k * plane) = o[k];
+                    for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(ps + k * planeB) = o[k];
                 }
             }
+            ps += rowB;
             // corner state of the next row
             Ej = E1;
             tyj = ty1;
             ty2 = ty3;
         }
+    };
+    for (int j0 = ja; j0 < jb; j0 += 3, bank ^= 1) {
+        if (j0 + 5 < Ny - 2) trip(std::true_type{}, j0);
+        else trip(std::false_type{}, j0);
     }
     cp_async_wait_all();
 
