@@ -250,6 +250,7 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 constexpr int NT = WPB * 32;
 
@@ -257,9 +258,10 @@ constexpr int NT = WPB * 32;
 // columns), so cp.async.wait_group is the only synchronisation: there is no barrier in the kernel.
 // The march is unrolled by 3 (the period of the 3-row register window), so a ring of depth 3 has compile-time
 // slots; depth-6 rings are 2 banks x 3 slots and the bank flips once per unrolled body.
-//   U : U^n rows.  Stage 2 reads row j again for the Heun average while row j+3 is in flight -> depth 6.
-//   D : dU rows (stage 2): row j+2 is consumed on arrival, row j+3 in flight            -> depth 3.
-//   E : bathymetry corner rows: j+1 (x faces), j+3 (arrived), j+4 (in flight)           -> depth 6.
+//   U : U^n rows.  Stage 2 reads row j again for the Heun average while rows j+3, j+4 are in flight -> depth 6
+//       (stage 1: depth 3).
+//   D : dU rows (stage 2): row j+2 is consumed on arrival, rows j+3, j+4 in flight            -> depth 3.
+//   E : bathymetry corner rows: j+1 (x faces), j+3 (arrived), j+4, j+5 (in flight)            -> depth 6.
 template <int STAGE>
 struct Rings {
     f2 U[STAGE == 2 ? 2 : 1][3][3][NT];      // [bank][slot][variable][thread]
@@ -417,10 +419,11 @@ __global__ void __launch_bounds__(NT, 4) k_stage_x2(const Args2 a) {
     const long long dOff = (const char*)a.D - (const char*)a.U;
     const char* pf = (const char*)(a.U + (size_t)(ja + 2) * Nx + xs);     // next state row to fetch
     const char* pc = (const char*)(a.B + (size_t)(ja + 3) * Bp + ic);     // next corner row to fetch
+    // two rows are in flight at any time (fetch distance 2): per-row BC bookkeeping of the generic path is a 2-deep queue
     char* ps = (char*)(a.out + (size_t)ja * Nx + i);                      // row j of the output
     const double* pfac = a.factor + (size_t)ja * Nx + ic;                 // Horton factor plane, row j
-    int ys_next = 0;                                      // BC source row of the state row in flight (generic path)
-    bool yflip_next = false, remap_next = false;
+    int ys_next = 0, ys_q = 0;                            // BC source row of the state rows in flight (generic path)
+    bool yflip_next = false, remap_next = false, yflip_q = false, remap_q = false;
     // ring addressing in bytes: this thread's 8-byte (4-byte for E2) column inside every [.. ][NT] row
     char* const smb = reinterpret_cast<char*>(&sm);
     constexpr unsigned U_BANK = 3 * 3 * NT * 8, U_SLOT = 3 * NT * 8, U_VAR = NT * 8;
@@ -433,9 +436,10 @@ __global__ void __launch_bounds__(NT, 4) k_stage_x2(const Args2 a) {
     auto fetch_row = [&](auto fast_tag, int row, unsigned ubank, int slot) {
         constexpr bool FAST = decltype(fast_tag)::value;
         const char* g = pf;
+        ys_q = ys_next; yflip_q = yflip_next; remap_q = remap_next;      // the row fetched one call ago
+        remap_next = false;
+        yflip_next = false;
         if (!FAST) {
-            remap_next = false;
-            yflip_next = false;
             ys_next = row;
             if (row >= Ny - 2) {                          // uniform
                 const int rr = min(row, Ny - 1);
@@ -464,6 +468,9 @@ __global__ void __launch_bounds__(NT, 4) k_stage_x2(const Args2 a) {
     fetch_row(std::false_type{}, ja + 2, 0u, 2);
     fetch_corner(std::false_type{}, ja + 3, E_BANK, E2_BANK, 0);
     cp_async_commit();
+    fetch_row(std::false_type{}, ja + 3, UB == 2 ? U_BANK : 0u, 0);
+    fetch_corner(std::false_type{}, ja + 4, E_BANK, E2_BANK, 1);
+    cp_async_commit();
 
     // ---- march: 3 rows per trip; rows beyond jb (last chunk only) are computed on clamped data and not stored ----
     int bank = 0;                                         // (j0 - ja) / 3 mod 2
@@ -479,11 +486,11 @@ __global__ void __launch_bounds__(NT, 4) k_stage_x2(const Args2 a) {
             f2* q0 = q[R];
             f2* q1 = q[(R + 1) % 3];
             f2* q2 = q[(R + 2) % 3];
-            // ---- arrivals: state row j+2 and corner row j+3 ----
-            cp_async_wait_all();
-            // (a FAST trip does not maintain ys_next / the flags: rows it fetched are never remapped)
-            const bool yflip2 = !FAST && yflip_next, remap2 = !FAST && remap_next;
-            const int ys2 = remap2 ? ys_next : j + 2;
+            // ---- arrivals: state row j+2 and corner row j+3 (rows j+3 / j+4 stay in flight) ----
+            cp_async_wait_1();
+            // (a FAST trip does not maintain the source rows: the rows it fetches are never remapped)
+            const bool yflip2 = !FAST && yflip_q, remap2 = !FAST && remap_q;
+            const int ys2 = remap2 ? ys_q : j + 2;
             f2 ru[3], rd[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -498,8 +505,8 @@ __global__ void __launch_bounds__(NT, 4) k_stage_x2(const Args2 a) {
                 E3.e = *reinterpret_cast<const f2*>(smE + uE[1] + R * E_SLOT);
                 E3.e2 = *reinterpret_cast<const float*>(smE2 + uE2[1] + R * E2_SLOT);
             }
-            fetch_row(fast_tag, j + 3, uU[1], R);          // in flight during this row's arithmetic
-            fetch_corner(fast_tag, j + 4, uE[((R + 4) / 3) & 1], uE2[((R + 4) / 3) & 1], (R + 1) % 3);
+            fetch_row(fast_tag, j + 4, uU[((R + 4) / 3) & 1], (R + 1) % 3);    // two rows ahead of the arrivals
+            fetch_corner(fast_tag, j + 5, uE[((R + 5) / 3) & 1], uE2[((R + 5) / 3) & 1], (R + 2) % 3);
             cp_async_commit();
             const f2 ty1 = ty_of(E1), ty3 = ty_of(E3);
             finish_row(remap2, ys2, yflip2, ru, rd, bcell(ty2, ty3), q2);
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(NT, 4) k_stage_x2(const Args2 a) {
         }
     };
     for (int j0 = ja; j0 < jb; j0 += 3, bank ^= 1) {
-        if (j0 + 5 < Ny - 2) trip(std::true_type{}, j0);
+        if (j0 + 6 < Ny - 2) trip(std::true_type{}, j0);
         else trip(std::false_type{}, j0);
     }
     cp_async_wait_all();
