@@ -3,11 +3,12 @@ library is missing or fails to load, importing the compute API raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = _CSRC / "libswe_b200.so"
+LIB_PATH = Path(os.environ.get("SWE_B200_LIB", _CSRC / "libswe_b200.so"))   # override: A/B builds
 
 ABI_VERSION = 1
 OK, EINVAL, EDOMAIN, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4

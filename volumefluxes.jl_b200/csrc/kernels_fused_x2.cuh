@@ -253,6 +253,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 constexpr int NT = WPB * 32;
+#ifndef X2_MINB
+#define X2_MINB 4
+#endif
 
 // Per-thread rings in shared memory.  Every thread only ever reads what it copied itself (its own two
 // columns), so cp.async.wait_group is the only synchronisation: there is no barrier in the kernel.
@@ -271,7 +274,7 @@ struct Rings {
 };
 
 template <int RECON, bool HASB, int STAGE, int FRIC, bool FACTOR>
-__global__ void __launch_bounds__(NT, 4) k_stage_x2(const Args2 a) {
+__global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
     __shared__ Rings<STAGE> sm;
     constexpr int UB = STAGE == 2 ? 2 : 1;               // banks of the U ring
     const Par2& p = a.p;
