@@ -229,6 +229,15 @@ def run_ours(args, rank, world):
     assert np.isfinite(out_pinned[0].numpy()).all()
     launches = sum_over_ranks(float(tm["launches"]))
     cells_local = n * rows
+    per_rank = None
+    if dist is not None:      # per-strip kernel times: shows the load imbalance behind the strong-scaling number
+        ns = max(tm["stage_launches"] // 2, 1)
+        mine = torch.tensor([tm["stage1_ms"] / ns, tm["stage2_ms"] / ns, tm["total_ms"] / args.steps, float(rows)],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"k1_ms": round(float(t[0]), 4), "k2_ms": round(float(t[1]), 4), "step_ms": round(float(t[2]), 4),
+                     "rows": int(t[3])} for t in allr]
     if rank != 0:
         barrier()
         if dist is not None:
@@ -286,6 +295,8 @@ def run_ours(args, rank, world):
                 "seconds": e2e_sec},
         "gpu_launches": int(launches), "setup_seconds": t_setup,
     }
+    if per_rank is not None:
+        out["per_rank"] = per_rank
     print(json.dumps(out), flush=True)
     barrier()
     if dist is not None:

@@ -191,6 +191,8 @@ public:
             q.rows = std::min(126, std::max(12, c.ny / std::max(1, want_by) / 3 * 3));
         }
         if (const char* e = std::getenv("SWE_B200_X2_ROWS")) q.rows = std::max(3, atoi(e) / 3 * 3);   // multiple of 3
+        q.ntiles = (c.nx + x2::VW - 1) / x2::VW;
+        q.nchunks = (c.ny + q.rows - 1) / q.rows;
         x2_ok = true;
     }
     template <int STAGE>
@@ -198,8 +200,9 @@ public:
         if constexpr (std::is_same<P, Policy<float, float, false>>::value) {
             x2::Args2 a;
             a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl;
-            const int ntiles = (cfg.nx + x2::VW - 1) / x2::VW;
-            dim3 g((ntiles + x2::WPB - 1) / x2::WPB, (cfg.ny + a.p.rows - 1) / a.p.rows);
+            // persistent warps pulling (tile, chunk) items: at most 4 blocks per SM are resident (128 registers)
+            const int items = a.p.ntiles * a.p.nchunks;
+            dim3 g(std::min((items + x2::WPB - 1) / x2::WPB, 148 * X2_MINB));
             dim3 b(x2::WPB * 32);
             const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
             const int fr = cfg.friction == SWE_B200_FRICTION_NONE ? 0 : (cfg.friction == SWE_B200_FRICTION_BH2021 ? 1 : 2);

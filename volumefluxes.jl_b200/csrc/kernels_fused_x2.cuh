@@ -65,6 +65,7 @@ struct Par2 {
     int Bp;                       // pitch of the corner array
     int bc, friction, bottom_source, ylo_phys, yhi_phys;
     int rain_kind, infil_kind, infil_first, rows;
+    int ntiles, nchunks;          // work items of one launch: ntiles x nchunks (tile: 60 output columns, chunk: `rows` rows)
     float cutoff, kappa, constB;
     f2 theta, half, mhalf, quarter, g, K /*0.5 rho g*/, i2k, hk, rho, nrdx, nrdy, botx, boty, Cz;
 };
@@ -280,12 +281,22 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
     const Par2& p = a.p;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int tile = blockIdx.x * WPB + (tid >> 5);
     const int Nx = p.Nx, Ny = p.Ny;
-    if (tile * VW + 2 >= Nx - 2) return;                 // warp-uniform: no output column
+    f2 msx = sp(0.0f), msy = sp(0.0f);                   // running CFL maxima of this thread (stage 1)
+    // Work queue: every WARP is independent (its own ring columns, no barrier), so warps pull (tile, chunk)
+    // items from one atomic counter until the grid is done.  That keeps all 148 SMs busy to the end of the
+    // launch although dry chunks finish ~40 % sooner than wet ones (no wave-quantisation tail).
+    const int total_items = p.ntiles * p.nchunks;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = (int)atomicAdd(&a.ctl->queue[STAGE - 1], 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total_items) break;
+    const int chunk = item / p.ntiles;
+    const int tile = item - chunk * p.ntiles;
     const int i = tile * VW + 2 * lane;                  // first of this lane's two columns (even)
     const int ic = min(i, Nx - 2);                       // clamped for loads (Nx is even)
-    const int ja = 2 + blockIdx.y * p.rows;
+    const int ja = 2 + chunk * p.rows;
     const int jb = min(ja + p.rows, Ny - 2);
     const bool in_x = i <= Nx - 4;
     const bool out_pair = lane >= 1 && lane <= 30 && in_x;
@@ -357,7 +368,6 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
     f2 dprev[3], Ry0[3], Gl[3], hsy;                      // y state of cell j: q(j+1)-q(j), upper face values, lower flux, hL+hR
     Corner Ej;                                            // corner row j
     f2 tyj, ty2;                                          // 2*B_face_y above corner rows j and j+2
-    f2 msx = sp(0.0f), msy = sp(0.0f);
     {
         Corner c[5];
 #pragma unroll
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
         f2 s = sp(0.0f);
         Gl[0] = Gl[1] = Gl[2] = sp(0.0f);
         if (__any_sync(0xffffffffu, any_wet(p, Rp[0], Ly0[0]))) cu2<1, STAGE == 1>(p, Rp, Ly0, Gl, s);   // face ja-1/2
-        if (STAGE == 1 && out_pair) msy = s;
+        if (STAGE == 1 && out_pair) { msy.x = fmaxf(msy.x, s.x); msy.y = fmaxf(msy.y, s.y); }
         hsy = add(Ly0[0], Ry0[0]);
         Ej = c[2];
         tyj = t0;
@@ -606,7 +616,8 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
         if (j0 + 6 < Ny - 2) trip(std::true_type{}, j0);
         else trip(std::false_type{}, j0);
     }
-    cp_async_wait_all();
+    cp_async_wait_all();                                  // the two rows fetched past the chunk: drain before the rings are reused
+  }   // work queue
 
     if (STAGE == 1) {
         // CFL reduction: warp shuffle -> one atomicMax per warp and direction (non-negative bit patterns)

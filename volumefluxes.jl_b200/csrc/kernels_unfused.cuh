@@ -26,6 +26,7 @@ struct Ctl {
     long long nsteps;     // steps taken with t < t_end
     int use_t_end;        // 1: inside simulate_to_time (t_end applies), 0: max_dt_host (perform_step!)
     int match_endtime;
+    unsigned int queue[2];  // work-queue heads of the two stage kernels of this step (kernels_fused_x2.cuh)
 };
 
 struct RainTable {
@@ -113,6 +114,8 @@ static __global__ void k_ctl_begin(Ctl* c, RainTable r, InfilPar f, double max_d
                             double t_end, double max_timestep) {
     c->maxspeed_bits[0] = 0ull;
     c->maxspeed_bits[1] = 0ull;
+    c->queue[0] = 0u;
+    c->queue[1] = 0u;
     c->max_dt_host = max_dt_host;
     c->use_t_end = use_t_end;
     c->match_endtime = match_endtime;
