@@ -104,6 +104,13 @@ def wet_fraction(case, state):
     return float(np.mean(state[0].astype(np.float64) - Bc >= case["depth_cutoff"]))
 
 
+def wet_fraction_rows(case, state):
+    """wet fraction of every interior row of a strip (input of the strip balancing cost model)"""
+    import cases
+    Bc = cases.synthetic().cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
+    return np.mean(state[0].astype(np.float64) - Bc >= case["depth_cutoff"], axis=1)
+
+
 def run_reference(args, rank):
     """The reference's CPU algorithm (oracle restatement: the Julia package cannot run here, see
     DESIGN.md) on the host cores, on a bounded crop of the same workload."""
@@ -157,9 +164,26 @@ def run_ours(args, rank, world):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.perf_counter()
+    balance = None
     if world > 1:
         case, state, y0 = cases.lake_strip_case(n, rank, world, dtype=args.dtype)
         rows = case["ny"]
+        if not args.equal_strips:
+            # load-balanced strips: every rank measures the wet fraction of the rows of its equal-height strip,
+            # the per-row vector is all-gathered, and every rank derives the same cost-equalising cuts
+            # (multigpu.partition_rows with row_cost); the strip is then generated again for its final rows.
+            wr = wet_fraction_rows(case, state)
+            sizes_eq = P.multigpu.partition_rows(n, world)[1]
+            buf = torch.zeros(max(sizes_eq), dtype=torch.float64, device="cuda")
+            buf[:rows] = torch.from_numpy(wr).cuda()
+            allw = [torch.zeros_like(buf) for _ in range(world)]
+            dist.all_gather(allw, buf)
+            wet_rows = np.concatenate([allw[r][:sizes_eq[r]].cpu().numpy() for r in range(world)])
+            offs, sizes = P.multigpu.partition_rows(n, world, P.multigpu.row_cost_from_wet_fraction(wet_rows, args.dry_cost))
+            balance = {"rows_per_rank": sizes, "dry_cost": args.dry_cost}
+            if (offs[rank], sizes[rank]) != (y0, rows):
+                case, state, y0 = cases.lake_strip_case(n, rank, world, dtype=args.dtype, rows=(offs[rank], sizes[rank]))
+                rows = case["ny"]
     else:
         case, state = build_case(n, args.dtype)
         y0, rows = 0, n
@@ -297,6 +321,8 @@ def run_ours(args, rank, world):
     }
     if per_rank is not None:
         out["per_rank"] = per_rank
+    if balance is not None:
+        out["config"]["strip_balance"] = balance
     print(json.dumps(out), flush=True)
     barrier()
     if dist is not None:
@@ -315,6 +341,10 @@ def main():
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--equal-strips", action="store_true", dest="equal_strips",
+                    help="N > 1: equal-height y-strips instead of the cost-balanced partition")
+    ap.add_argument("--dry-cost", type=float, default=0.6, dest="dry_cost",
+                    help="cost of a dry cell relative to a wet one in the strip balancing model")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -239,13 +239,17 @@ def field_errors(a, b):
             float(np.max(np.abs(a[2] - b[2])) / dm)]
 
 
-def lake_strip_case(n, rank, nranks, dtype="float32", level=0.0, wavelength=512.0, cutoff=1e-3):
+def lake_strip_case(n, rank, nranks, dtype="float32", level=0.0, wavelength=512.0, cutoff=1e-3, rows=None):
     """config 5 generated directly as the y-strip of `rank` (no rank ever materialises the global arrays).
+    `rows` = (y_offset, n_rows) overrides the equal-height partition (load-balanced strips).
     Returns (strip case dict, strip state, y_offset)."""
     from_pkg = load_package()
     syn = from_pkg.synthetic
-    offsets, sizes = from_pkg.multigpu.partition_rows(n, nranks)
-    y0, nr = offsets[rank], sizes[rank]
+    if rows is None:
+        offsets, sizes = from_pkg.multigpu.partition_rows(n, nranks)
+        y0, nr = offsets[rank], sizes[rank]
+    else:
+        y0, nr = rows
     npd = np.dtype(dtype)
     B = syn.terrain_corners(n, n, 2, seed=1234, dtype=npd, wavelength=wavelength, row_range=(y0, y0 + nr + 5))
     case = dict(dim=2, dtype=dtype, nx=n, ny=nr, gc=2, bc="wall", extent=[0.0, float(n), 0.0, float(n)],

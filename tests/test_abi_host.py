@@ -89,3 +89,19 @@ def test_synthetic_terrain_is_deterministic():
     assert np.ptp(a) > 0.5 and np.abs(np.diff(a, axis=1)).max() < 0.5
     c = syn.cell_average(a)
     assert c.shape == (52, 68)
+
+
+def test_cost_balanced_partition(pkg):
+    """multigpu.partition_rows: equal heights without a cost; cost-equalising cuts with one (the dt all-gather
+    makes every rank wait for the slowest strip, so strips are cut by estimated work, not by rows)"""
+    mg = pkg.multigpu
+    assert mg.partition_rows(83, 3) == ([0, 28, 56], [28, 28, 27])
+    wet = np.r_[np.zeros(40), np.ones(43)]
+    offs, sizes = mg.partition_rows(83, 3, mg.row_cost_from_wet_fraction(wet, dry_cost=0.5))
+    assert offs[0] == 0 and sum(sizes) == 83 and sizes[0] > sizes[2]          # dry rows are cheaper -> taller strip
+    cost = mg.row_cost_from_wet_fraction(wet, dry_cost=0.5)
+    work = [cost[o:o + n].sum() for o, n in zip(offs, sizes)]
+    assert max(work) - min(work) <= 2 * cost.max()
+    assert mg.partition_rows(16, 4, np.r_[np.zeros(12), np.ones(4)])[1] == [4, 4, 4, 4]   # never below 4 rows
+    with pytest.raises(pkg.ArgumentError):
+        mg.partition_rows(83, 3, np.ones(82))

@@ -72,6 +72,24 @@ def test_fast_strips_match_single_domain(P):
         assert np.array_equal(a, b)
 
 
+def test_cost_balanced_strips_bitwise(P):
+    """unequal strip heights (multigpu.partition_rows with a per-row cost) reproduce the single-domain run too"""
+    case, state = CASES["lake_wall_rk2"]("float64")
+    ny = case["ny"]
+    cost = P.multigpu.row_cost_from_wet_fraction(np.linspace(0.0, 1.0, ny) ** 2)
+    offs, sizes = P.multigpu.partition_rows(ny, 3, cost)
+    assert sum(sizes) == ny and len(set(sizes)) > 1 and min(sizes) >= 4
+    single = P.simulator_from_case(case, strict=True)
+    single.set_state_interior(*state)
+    single.run_steps(15)
+    grp = P.multigpu.LocalStripGroup(case, state, devices_for(3), strict=True, row_cost=cost)
+    assert [n for _, n in grp.rows] == sizes
+    grp.run_steps(15)
+    for a, b in zip(grp.gather_interior(), single.get_state_interior()):
+        assert np.array_equal(a, b)
+    assert grp.t == single.t
+
+
 def test_partition_and_errors(P):
     off, sz = P.multigpu.partition_rows(83, 3)
     assert sz == [28, 28, 27] and off == [0, 28, 56]

@@ -81,6 +81,17 @@ public:
     std::vector<cudaEvent_t> ev;   // per-stage-kernel timing events (timed runs only)
     std::vector<int> ev_stage;
     bool timing_on = false;
+    bool trace_on = false;                       // SWE_B200_TRACE=1: per-launch timeline of the timed steps (stderr)
+    std::vector<cudaEvent_t> tr_ev;
+    std::vector<const char*> tr_label;
+    void mark(const char* label) {
+        if (!(timing_on && trace_on)) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        tr_ev.push_back(e);
+        tr_label.push_back(label);
+    }
 
     int init(const swe_b200_config& c) {
         cfg = c;
@@ -523,7 +534,7 @@ public:
     }
     // ---- multi-GPU: peer pushes of halo rows / CFL maxima (kernels_exchange.cuh) -------------------------
     // kind 0: dU rows (stamp slots 0/1), kind 2: U rows (slots 2/3); rows_only=false also publishes the speeds
-    void push_halo(const S* src, int vol_index, int kind, bool with_speed, bool rows = true) {
+    void push_halo(const S* src, int vol_index, int kind, bool with_speed, bool rows = true, bool with_dt = false) {
         PushArgs<S> a{};
         a.src = src;
         a.src_plane = plane;
@@ -545,9 +556,16 @@ public:
         a.nranks = cfg.nranks; a.rank = cfg.rank; a.seq = sseq; a.ctl = ctl;
         for (int r = 0; r < cfg.nranks; ++r) a.mbox[r] = peer_mbox[r];
         a.ticket = ticket;
-        const long long total = (long long)a.rows * Nx * 6;
-        const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 64));
-        k_halo_push<S><<<blocks, 256, 0, stream>>>(a);
+        a.ctl_rw = ctl;
+        a.dt.enabled = with_dt ? 1 : 0;
+        if (with_dt) {      // the last block of the push also gathers the maxima and computes dt (was k_ctl_dt_multi)
+            a.dt.dx = par_dx(); a.dt.dy = par_dy(); a.dt.cfl = (double)(S)cfg.cfl;
+            a.dt.nranks = cfg.nranks; a.dt.has_lo = lo_rank >= 0; a.dt.has_hi = hi_rank >= 0;
+            a.dt.seq = sseq; a.dt.dU_stamp = rows ? a.stamp : 0ull;
+        }
+        const long long per_side = (long long)a.rows * Nx;
+        const int bx = (int)std::max<long long>(1, std::min<long long>((per_side / 4 + 255) / 256, 8));
+        k_halo_push<S><<<dim3(bx, a.rows > 0 ? 6 : 1), 256, 0, stream>>>(a);
         ++launches;
         if (rows && kind == 2) pending_U = a.stamp;
     }
@@ -556,28 +574,26 @@ public:
         const bool multi = peers_open;
         S* U = vol[cur[0]];
         S* D = vol[cur[1]];
-        if (multi && pending_U) {   // the neighbours' U rows of the previous exchange must have landed
-            k_wait_halo<<<1, 1, 0, stream>>>(mbox, 2, lo_rank >= 0, hi_rank >= 0, pending_U);
-            ++launches;
-            pending_U = 0;
-        }
+        mark("ctl_begin");
         launch_stage<1>(U, nullptr, D);
+        mark("K1");
         const bool rk2 = cfg.stepper == SWE_B200_RK2;
         if (multi) {
             ++sseq;
-            push_halo(D, cur[1], 0, true, rk2);     // dU rows (RK2 only) + this rank's CFL maxima
-            k_ctl_dt_multi<S><<<1, 1, 0, stream>>>(ctl, mbox, par_dx(), par_dy(), (S)cfg.cfl, cfg.nranks, sseq,
-                                                   lo_rank >= 0, hi_rank >= 0, rk2 ? xseq : 0ull);
+            // dU rows (RK2 only) + this rank's CFL maxima; the same launch then gathers all maxima -> dt
+            push_halo(D, cur[1], 0, true, rk2, true);
         } else {
             k_ctl_dt<S><<<1, 1, 0, stream>>>(ctl, par_dx(), par_dy(), (S)cfg.cfl);
         }
         ++launches;
+        mark("dt(+push dU)");
         S* next;
         int next_index;
         if (rk2) {
             next = vol[cur[2]];
             next_index = cur[2];
             launch_stage<2>(U, D, next);
+            mark("K2");
             std::swap(cur[0], cur[2]);
         } else {
             dim3 b(32, 8), g((cfg.nx + 31) / 32, (cfg.ny + 7) / 8);
@@ -588,14 +604,23 @@ public:
             next_index = cur[1];
             std::swap(cur[0], cur[1]);
         }
+        // the owned boundary rows go to the neighbours first: no consumer reads the x-ghost columns of a halo
+        // row from memory (both stage kernels remap them), so the push need not wait for the ghost fill
+        if (multi) { push_halo(next, next_index, 2, false); mark("push U"); }
         const int nthreads = (Ny - 2 * gc) + (Nx - 2 * gc);
         k_bc_advance<S><<<(nthreads + 127) / 128, 128, 0, stream>>>(next, Nx, Ny, plane, gc, cfg.bc, par.ylo_phys,
                                                                     par.yhi_phys, ctl, advance);
         ++launches;
-        if (multi) push_halo(next, next_index, 2, false);
+        mark("bc_advance");
     }
     void one_step(double max_dt_host, int use_t_end, int match, double t_end, double max_timestep, int advance) {
-        k_ctl_begin<<<1, 1, 0, stream>>>(ctl, rt, ip, max_dt_host, use_t_end, match, t_end, max_timestep);
+        if (peers_open && fused_ok && pending_U) {   // + wait for the neighbours' U rows of the previous exchange
+            k_ctl_begin_multi<<<1, 1, 0, stream>>>(ctl, rt, ip, max_dt_host, use_t_end, match, t_end, max_timestep, mbox,
+                                                   lo_rank >= 0, hi_rank >= 0, pending_U);
+            pending_U = 0;
+        } else {
+            k_ctl_begin<<<1, 1, 0, stream>>>(ctl, rt, ip, max_dt_host, use_t_end, match, t_end, max_timestep);
+        }
         ++launches;
         if (fused_ok) step_fused(advance);
         else step_unfused(advance);
@@ -621,6 +646,8 @@ public:
             SWE_CUDA(cudaEventCreate(&t0));
             SWE_CUDA(cudaEventCreate(&t1));
             timing_on = true;
+            { const char* e = std::getenv("SWE_B200_TRACE"); trace_on = e && e[0] == '1'; }
+            mark("start");
             SWE_CUDA(cudaStreamSynchronize(stream));
             SWE_CUDA(cudaEventRecord(t0, stream));
         }
@@ -629,6 +656,21 @@ public:
             SWE_CUDA(cudaEventRecord(t1, stream));
             SWE_CUDA(cudaStreamSynchronize(stream));
             timing_on = false;
+            if (trace_on && tr_ev.size() > 1) {
+                std::vector<std::pair<const char*, double>> acc2;
+                for (size_t q = 1; q < tr_ev.size(); ++q) {
+                    float m = 0;
+                    cudaEventElapsedTime(&m, tr_ev[q - 1], tr_ev[q]);
+                    bool found = false;
+                    for (auto& pr : acc2) if (pr.first == tr_label[q]) { pr.second += m; found = true; }
+                    if (!found) acc2.push_back({tr_label[q], (double)m});
+                }
+                fprintf(stderr, "[swe_b200 trace rank %d] per step (us):", cfg.rank);
+                for (auto& pr : acc2) fprintf(stderr, " %s=%.1f", pr.first, 1e3 * pr.second / (double)n);
+                fprintf(stderr, "\n");
+                for (auto e : tr_ev) cudaEventDestroy(e);
+                tr_ev.clear(); tr_label.clear();
+            }
             float ms = 0;
             SWE_CUDA(cudaEventElapsedTime(&ms, t0, t1));
             timing->total_ms = ms;

@@ -20,64 +20,6 @@ struct Mailbox {
     unsigned long long timeout;                    // != 0: a wait gave up (reported by the host as an error)
 };
 
-template <class S>
-struct PushArgs {
-    const S* src;            // local volume (3 planes)
-    S* dst_lo;               // lower neighbour's volume (peer pointer) or nullptr
-    S* dst_hi;               // upper neighbour's volume (peer pointer) or nullptr
-    long long src_plane, lo_plane, hi_plane;
-    int Nx, Ny, gc, lo_Ny;   // lo_Ny: total rows of the lower neighbour's strip
-    int rows;                // 0: no halo rows (speeds only)
-    unsigned long long* flag_lo;   // in the lower neighbour's mailbox: "from upper" stamp
-    unsigned long long* flag_hi;   // in the upper neighbour's mailbox: "from lower" stamp
-    unsigned long long stamp;
-    int with_speed, nranks, rank;
-    unsigned long long seq;
-    const Ctl* ctl;
-    Mailbox* mbox[MAX_RANKS];      // every rank's mailbox (own included)
-    unsigned int* ticket;          // local counter for last-block detection
-};
-
-template <class S>
-__global__ void k_halo_push(const PushArgs<S> a) {
-    const long long per_side = (long long)a.rows * a.Nx;        // elements per plane and side
-    const long long total = per_side * 3 * 2;
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
-         q += (long long)gridDim.x * blockDim.x) {
-        const int side = (int)(q / (per_side * 3));
-        const long long r = q - side * per_side * 3;
-        const int k = (int)(r / per_side);
-        const long long e = r - k * per_side;                   // row-major within the gc rows
-        if (side == 0) {   // my lowest owned rows -> lower neighbour's top ghost rows
-            if (a.dst_lo) a.dst_lo[k * a.lo_plane + (long long)(a.lo_Ny - a.gc) * a.Nx + e] =
-                              a.src[k * a.src_plane + (long long)a.gc * a.Nx + e];
-        } else {           // my highest owned rows -> upper neighbour's bottom ghost rows
-            if (a.dst_hi) a.dst_hi[k * a.hi_plane + e] =
-                              a.src[k * a.src_plane + (long long)(a.Ny - 2 * a.gc) * a.Nx + e];
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    if (threadIdx.x == 0) *a.ticket = 0;
-    __threadfence_system();
-    if (a.rows > 0) {
-        if (threadIdx.x == 0 && a.flag_lo) *(volatile unsigned long long*)a.flag_lo = a.stamp;
-        if (threadIdx.x == 1 && a.flag_hi) *(volatile unsigned long long*)a.flag_hi = a.stamp;
-    }
-    if (a.with_speed && threadIdx.x < a.nranks) {
-        Mailbox* m = a.mbox[threadIdx.x];
-        const int par = (int)(a.seq & 1ull);
-        m->speed[par][a.rank][0] = a.ctl->maxspeed_bits[0];
-        m->speed[par][a.rank][1] = a.ctl->maxspeed_bits[1];
-        __threadfence_system();
-        *(volatile unsigned long long*)&m->speed_stamp[par][a.rank] = a.seq;
-    }
-}
-
 __device__ __forceinline__ bool spin_until(volatile unsigned long long* p, unsigned long long want, Mailbox* mb) {
     const long long t0 = clock64();
     while (*p < want) {
@@ -100,16 +42,27 @@ __device__ __forceinline__ void wait_halo(Mailbox* mb, int base, int has_lo, int
 static __global__ void k_wait_halo(Mailbox* mb, int base, int has_lo, int has_hi, unsigned long long stamp) {
     wait_halo(mb, base, has_lo, has_hi, stamp);
 }
+// start of a multi-GPU step in one launch: k_ctl_begin + the wait for the neighbours' U rows of the last exchange
+static __global__ void k_ctl_begin_multi(Ctl* c, RainTable r, InfilPar f, double max_dt_host, int use_t_end,
+                                         int match_endtime, double t_end, double max_timestep, Mailbox* mb, int has_lo,
+                                         int has_hi, unsigned long long U_stamp) {
+    ctl_begin(c, r, f, max_dt_host, use_t_end, match_endtime, t_end, max_timestep);
+    if (U_stamp) wait_halo(mb, 2, has_lo, has_hi, U_stamp);
+}
 
 // multi-rank timestep: gather all ranks' maxima from the mailbox, then timestep_computer as in k_ctl_dt,
 // then wait for the dU halo rows stage 2 needs.
+struct DtArgs {
+    double dx, dy, cfl;           // cfl already rounded to the realtype
+    int enabled, nranks, has_lo, has_hi;
+    unsigned long long seq, dU_stamp;
+};
 template <class S>
-__global__ void k_ctl_dt_multi(Ctl* c, Mailbox* mb, double dx, double dy, S cfl, int nranks, unsigned long long seq,
-                               int has_lo, int has_hi, unsigned long long dU_stamp) {
-    const int par = (int)(seq & 1ull);
+__device__ __forceinline__ void ctl_dt_multi(Ctl* c, Mailbox* mb, const DtArgs& d) {
+    const int par = (int)(d.seq & 1ull);
     unsigned long long bx = 0ull, by = 0ull;
-    for (int r = 0; r < nranks; ++r) {
-        spin_until(&mb->speed_stamp[par][r], seq, mb);
+    for (int r = 0; r < d.nranks; ++r) {
+        spin_until(&mb->speed_stamp[par][r], d.seq, mb);
         const unsigned long long x = *(volatile unsigned long long*)&mb->speed[par][r][0];
         const unsigned long long y = *(volatile unsigned long long*)&mb->speed[par][r][1];
         bx = x > bx ? x : bx;
@@ -119,17 +72,91 @@ __global__ void k_ctl_dt_multi(Ctl* c, Mailbox* mb, double dx, double dy, S cfl,
     c->maxspeed_bits[1] = by;
     const S ax = Bits<S>::dec(bx);
     const S ay = Bits<S>::dec(by);
-    double ddt = fmin(dx / ax, dy / ay);
+    double ddt = fmin(d.dx / ax, d.dy / ay);
     double max_dt = c->max_dt_host;
     if (c->use_t_end) max_dt = c->match_endtime ? (c->t_end - c->t) : (double)INFINITY;
     if (c->max_timestep > 0) max_dt = fmin(max_dt, c->max_timestep);
-    double dt = fmin(cfl * ddt, max_dt);
+    double dt = fmin((S)d.cfl * ddt, max_dt);
     const bool past_end = c->use_t_end && !(c->t < c->t_end);
     if (past_end) dt = 0.0;
     c->dt = dt;
     c->dt_s = (double)(S)dt;
     if (!past_end) c->dt_report = c->dt_s;
-    if (dU_stamp) wait_halo(mb, 0, has_lo, has_hi, dU_stamp);
+    if (d.dU_stamp) wait_halo(mb, 0, d.has_lo, d.has_hi, d.dU_stamp);
+}
+
+template <class S>
+struct PushArgs {
+    const S* src;            // local volume (3 planes)
+    S* dst_lo;               // lower neighbour's volume (peer pointer) or nullptr
+    S* dst_hi;               // upper neighbour's volume (peer pointer) or nullptr
+    long long src_plane, lo_plane, hi_plane;
+    int Nx, Ny, gc, lo_Ny;   // lo_Ny: total rows of the lower neighbour's strip
+    int rows;                // 0: no halo rows (speeds only)
+    unsigned long long* flag_lo;   // in the lower neighbour's mailbox: "from upper" stamp
+    unsigned long long* flag_hi;   // in the upper neighbour's mailbox: "from lower" stamp
+    unsigned long long stamp;
+    int with_speed, nranks, rank;
+    unsigned long long seq;
+    const Ctl* ctl;
+    Mailbox* mbox[MAX_RANKS];      // every rank's mailbox (own included)
+    unsigned int* ticket;          // local counter for last-block detection
+    Ctl* ctl_rw;                   // for the fused timestep
+    DtArgs dt;                     // dt.enabled: the last block also computes the step's dt (was a launch of its own)
+};
+
+template <class S>
+__global__ void k_halo_push(const PushArgs<S> a) {
+    // blockIdx.y = side * 3 + plane: each (side, plane) is ONE contiguous run of rows*Nx elements on both ends
+    // (the gc boundary rows are adjacent in memory), copied with 16-byte peer stores when the runs are aligned.
+    const long long per_side = (long long)a.rows * a.Nx;
+    if (per_side > 0) {
+        const int side = blockIdx.y / 3, k = blockIdx.y - 3 * side;
+        const S* src;
+        S* dst;
+        if (side == 0) {   // my lowest owned rows -> lower neighbour's top ghost rows
+            src = a.src + k * a.src_plane + (long long)a.gc * a.Nx;
+            dst = a.dst_lo ? a.dst_lo + k * a.lo_plane + (long long)(a.lo_Ny - a.gc) * a.Nx : nullptr;
+        } else {           // my highest owned rows -> upper neighbour's bottom ghost rows
+            src = a.src + k * a.src_plane + (long long)(a.Ny - 2 * a.gc) * a.Nx;
+            dst = a.dst_hi ? a.dst_hi + k * a.hi_plane : nullptr;
+        }
+        if (dst) {
+            const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+            constexpr int V = 16 / sizeof(S);
+            if ((((unsigned long long)src | (unsigned long long)dst) & 15ull) == 0 && per_side % V == 0) {
+                const int4* s4 = reinterpret_cast<const int4*>(src);
+                int4* d4 = reinterpret_cast<int4*>(dst);
+                for (long long q = t; q < per_side / V; q += nt) d4[q] = s4[q];
+            } else {
+                for (long long q = t; q < per_side; q += nt) dst[q] = src[q];
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *a.ticket = 0;
+    __threadfence_system();
+    if (a.rows > 0) {
+        if (threadIdx.x == 0 && a.flag_lo) *(volatile unsigned long long*)a.flag_lo = a.stamp;
+        if (threadIdx.x == 1 && a.flag_hi) *(volatile unsigned long long*)a.flag_hi = a.stamp;
+    }
+    if (a.with_speed && threadIdx.x < a.nranks) {
+        Mailbox* m = a.mbox[threadIdx.x];
+        const int par = (int)(a.seq & 1ull);
+        m->speed[par][a.rank][0] = a.ctl->maxspeed_bits[0];
+        m->speed[par][a.rank][1] = a.ctl->maxspeed_bits[1];
+        __threadfence_system();
+        *(volatile unsigned long long*)&m->speed_stamp[par][a.rank] = a.seq;
+    }
+    if (a.dt.enabled) {
+        __syncthreads();
+        if (threadIdx.x == 0) ctl_dt_multi<S>(a.ctl_rw, a.mbox[a.rank], a.dt);
+    }
 }
 
 }  // namespace swe

@@ -110,8 +110,8 @@ __device__ __forceinline__ void ctl_rates(Ctl* c, const RainTable& r, const Infi
     c->infil = inf;
 }
 
-static __global__ void k_ctl_begin(Ctl* c, RainTable r, InfilPar f, double max_dt_host, int use_t_end, int match_endtime,
-                            double t_end, double max_timestep) {
+__device__ __forceinline__ void ctl_begin(Ctl* c, const RainTable& r, const InfilPar& f, double max_dt_host, int use_t_end,
+                                          int match_endtime, double t_end, double max_timestep) {
     c->maxspeed_bits[0] = 0ull;
     c->maxspeed_bits[1] = 0ull;
     c->queue[0] = 0u;
@@ -122,6 +122,10 @@ static __global__ void k_ctl_begin(Ctl* c, RainTable r, InfilPar f, double max_d
     c->t_end = t_end;
     c->max_timestep = max_timestep;
     ctl_rates(c, r, f);
+}
+static __global__ void k_ctl_begin(Ctl* c, RainTable r, InfilPar f, double max_dt_host, int use_t_end, int match_endtime,
+                                   double t_end, double max_timestep) {
+    ctl_begin(c, r, f, max_dt_host, use_t_end, match_endtime, t_end, max_timestep);
 }
 
 // timestep_computer (simulator.jl:147-150): dt = min(cfl*min(dx/ax, dy/ay), max_dt), with
