@@ -168,7 +168,7 @@ public:
         for (int r = 0; r < MAX_RANKS; ++r)
             if (peer_ipc[r] && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
         cudaFree(slab);
-        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl);
+        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl); cudaFree(d_items);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (auto e : ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -195,24 +195,64 @@ public:
         q.g = s2(c.g); q.K = s2(0.5 * c.rho * c.g); q.i2k = s2(1.0 / (2 * c.kappa)); q.hk = s2(c.kappa / 2.0);
         q.rho = s2(c.rho); q.nrdx = s2(-1.0 / dx); q.nrdy = s2(-1.0 / dy);
         q.botx = s2(c.has_bottom_source ? -0.25 * c.g / dx : 0.0); q.boty = s2(c.has_bottom_source ? -0.25 * c.g / dy : 0.0); q.Cz = s2(c.Cz);
-        {   // rows per block: a multiple of 3 (the march is unrolled by 3), long chunks on large grids (the 4-row
-            // prologue amortises), but at least ~2 waves of 4 blocks per SM on small ones
-            const int ntiles = (c.nx + x2::VW - 1) / x2::VW, bx = (ntiles + x2::WPB - 1) / x2::WPB;
-            const int want_by = (148 * 4 * 2 + bx - 1) / bx;
-            q.rows = std::min(126, std::max(12, c.ny / std::max(1, want_by) / 3 * 3));
-        }
+        q.rows = 126;
         if (const char* e = std::getenv("SWE_B200_X2_ROWS")) q.rows = std::max(3, atoi(e) / 3 * 3);   // multiple of 3
-        q.ntiles = (c.nx + x2::VW - 1) / x2::VW;
-        q.nchunks = (c.ny + q.rows - 1) / q.rows;
+        build_items(c, q.rows);
         x2_ok = true;
     }
+    // Guided schedule of the persistent warps: every tile column (60 output columns) is cut into row segments;
+    // most rows go into `big`-row items (the 4-row prologue amortises), the rest into three classes of ever
+    // smaller items that are handed out LAST, sized so that each of the 148*4*4 resident warps gets about one
+    // 63-, one 30- and two 12-row items: the launch then ends within about half a small item everywhere.
+    int4* d_items = nullptr;
+    int n_items = 0;
+    void build_items(const swe_b200_config& c, int big) {
+        const int ntiles = (c.nx + x2::VW - 1) / x2::VW;
+        const long long W = 148LL * X2_MINB * x2::WPB;
+        const long long L = (long long)ntiles * c.ny;
+        int sizes[4] = {big, 63, 30, 12};
+        long long quota[4];
+        quota[3] = std::min(L / 8, W * 2 * sizes[3]);
+        quota[2] = std::min(L / 6, W * 1 * sizes[2]);
+        quota[1] = std::min(L / 4, W * 1 * sizes[1]);
+        if (const char* e = std::getenv("SWE_B200_X2_FLAT")) { if (e[0] == '1') quota[1] = quota[2] = quota[3] = 0; }
+        quota[0] = L - quota[1] - quota[2] - quota[3];
+        // rows of every tile column per class, top of the column = smallest items (any order works: the classes
+        // are emitted class by class, tile-fastest, so neighbours in x run at about the same time -> L2 reuse)
+        std::vector<int4> items;
+        std::vector<int> pos(ntiles, 0);
+        for (int k = 0; k < 4; ++k) {
+            // per column share of this class, in whole items; the last class takes whatever is left
+            const long long per_col = quota[k] / ntiles / sizes[k] * sizes[k];
+            std::vector<int> lim(ntiles);
+            for (int t = 0; t < ntiles; ++t) lim[t] = k == 3 ? c.ny : (int)std::min<long long>(c.ny, pos[t] + per_col);
+            bool any = true;
+            while (any) {
+                any = false;
+                for (int t = 0; t < ntiles; ++t) {
+                    if (pos[t] >= lim[t]) continue;
+                    const int n = std::min(sizes[k], c.ny - pos[t]);
+                    if (k < 3 && pos[t] + n > lim[t]) continue;
+                    items.push_back(make_int4(t, 2 + pos[t], n, 0));
+                    pos[t] += n;
+                    any = true;
+                }
+            }
+        }
+        n_items = (int)items.size();
+        if (d_items) cudaFree(d_items);
+        cudaMalloc(&d_items, sizeof(int4) * items.size());
+        cudaMemcpy(d_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice);
+        par2.nitems = n_items;
+    }
+
     template <int STAGE>
     void launch_stage_x2(const S* U, const S* D, S* out) {
         if constexpr (std::is_same<P, Policy<float, float, false>>::value) {
             x2::Args2 a;
-            a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl;
-            // persistent warps pulling (tile, chunk) items: at most 4 blocks per SM are resident (128 registers)
-            const int items = a.p.ntiles * a.p.nchunks;
+            a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl; a.items = d_items;
+            // persistent warps pulling (tile, rows) items: at most 4 blocks per SM are resident (128 registers)
+            const int items = n_items;
             dim3 g(std::min((items + x2::WPB - 1) / x2::WPB, 148 * X2_MINB));
             dim3 b(x2::WPB * 32);
             const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;

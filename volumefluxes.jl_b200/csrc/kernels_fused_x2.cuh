@@ -65,7 +65,7 @@ struct Par2 {
     int Bp;                       // pitch of the corner array
     int bc, friction, bottom_source, ylo_phys, yhi_phys;
     int rain_kind, infil_kind, infil_first, rows;
-    int ntiles, nchunks;          // work items of one launch: ntiles x nchunks (tile: 60 output columns, chunk: `rows` rows)
+    int nitems;                   // work items of one launch (Args2::items)
     float cutoff, kappa, constB;
     f2 theta, half, mhalf, quarter, g, K /*0.5 rho g*/, i2k, hk, rho, nrdx, nrdy, botx, boty, Cz;
 };
@@ -78,6 +78,7 @@ struct Args2 {
     const float* B;
     const double* factor;
     Ctl* ctl;
+    const int4* items;            // (tile, first interior row, number of rows (multiple of 3 except at the top), 0)
 };
 
 // ---- minmod(a,b,c), linearreconstruction.jl:28-35, as the median of (min3, 0, max3) ----------------
@@ -283,21 +284,22 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
     const int lane = tid & 31;
     const int Nx = p.Nx, Ny = p.Ny;
     f2 msx = sp(0.0f), msy = sp(0.0f);                   // running CFL maxima of this thread (stage 1)
-    // Work queue: every WARP is independent (its own ring columns, no barrier), so warps pull (tile, chunk)
-    // items from one atomic counter until the grid is done.  That keeps all 148 SMs busy to the end of the
-    // launch although dry chunks finish ~40 % sooner than wet ones (no wave-quantisation tail).
-    const int total_items = p.ntiles * p.nchunks;
+    // Work queue: every WARP is independent (its own ring columns, no barrier), so warps pull (tile, rows)
+    // items from one atomic counter until the grid is done.  The item table is a guided schedule (EngineT::
+    // build_items): 126-row items first, then 63-, 30- and 12-row items, so that all 148 SMs stay busy to the
+    // end of the launch although dry stretches finish ~40 % sooner than wet ones.
+    const int total_items = p.nitems;
   for (;;) {
     int item = 0;
     if (lane == 0) item = (int)atomicAdd(&a.ctl->queue[STAGE - 1], 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total_items) break;
-    const int chunk = item / p.ntiles;
-    const int tile = item - chunk * p.ntiles;
+    const int4 it = a.items[item];                       // (tile, first row, rows, -): guided schedule, large items first
+    const int tile = it.x;
     const int i = tile * VW + 2 * lane;                  // first of this lane's two columns (even)
     const int ic = min(i, Nx - 2);                       // clamped for loads (Nx is even)
-    const int ja = 2 + chunk * p.rows;
-    const int jb = min(ja + p.rows, Ny - 2);
+    const int ja = it.y;
+    const int jb = min(ja + it.z, Ny - 2);
     const bool in_x = i <= Nx - 4;
     const bool out_pair = lane >= 1 && lane <= 30 && in_x;
     const bool facea_ok = out_pair;                      // face (i | i+1)   belongs to an interior cell
@@ -363,6 +365,68 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
         }
     };
 
+    // ---- fetch of state row r / corner row r into the rings (the first two rows of the march are requested
+    // before the prologue's own loads are consumed, so the item start exposes one memory latency, not two) ----
+    // Running byte pointers advance by one row per fetch.  A trip (3 rows) is FAST when every row it fetches is
+    // an interior row (no y-BC remap, no clamping, every row stored); only the last trip(s) of the last chunk
+    // take the generic path.
+    const long long rowB = (long long)Nx * 4, planeB = plane * 4;
+    const long long dOff = (const char*)a.D - (const char*)a.U;
+    const char* pf = (const char*)(a.U + (size_t)(ja + 2) * Nx + xs);     // next state row to fetch
+    const char* pc = (const char*)(a.B + (size_t)(ja + 3) * Bp + ic);     // next corner row to fetch
+    // two rows are in flight at any time (fetch distance 2): per-row BC bookkeeping of the generic path is a 2-deep queue
+    char* ps = (char*)(a.out + (size_t)ja * Nx + i);                      // row j of the output
+    const double* pfac = a.factor + (size_t)ja * Nx + ic;                 // Horton factor plane, row j
+    int ys_next = 0, ys_q = 0;                            // BC source row of the state rows in flight (generic path)
+    bool yflip_next = false, remap_next = false, yflip_q = false, remap_q = false;
+    // ring addressing in bytes: this thread's 8-byte (4-byte for E2) column inside every [.. ][NT] row
+    char* const smb = reinterpret_cast<char*>(&sm);
+    constexpr unsigned U_BANK = 3 * 3 * NT * 8, U_SLOT = 3 * NT * 8, U_VAR = NT * 8;
+    constexpr unsigned D_OFF = offsetof(Rings<STAGE>, D), E_OFF = offsetof(Rings<STAGE>, E), E2_OFF = offsetof(Rings<STAGE>, E2);
+    constexpr unsigned E_BANK = 3 * NT * 8, E_SLOT = NT * 8, E2_BANK = 3 * NT * 4, E2_SLOT = NT * 4;
+    char* const smU = smb + tid * 8;
+    char* const smD = smb + D_OFF + tid * 8;
+    char* const smE = smb + E_OFF + tid * 8;
+    char* const smE2 = smb + E2_OFF + tid * 4;
+    auto fetch_row = [&](auto fast_tag, int row, unsigned ubank, int slot) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        const char* g = pf;
+        ys_q = ys_next; yflip_q = yflip_next; remap_q = remap_next;      // the row fetched one call ago
+        remap_next = false;
+        yflip_next = false;
+        if (!FAST) {
+            ys_next = row;
+            if (row >= Ny - 2) {                          // uniform
+                const int rr = min(row, Ny - 1);
+                ys_next = row_source(rr, yflip_next);
+                remap_next = ys_next != row;
+                g = (const char*)(a.U + (size_t)ys_next * Nx + xs);
+            }
+        }
+        pf += rowB;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            cp_async8(smU + ubank + slot * U_SLOT + k * U_VAR, g + k * planeB);
+            if (STAGE == 2) cp_async8(smD + slot * U_SLOT + k * U_VAR, g + dOff + k * planeB);
+        }
+    };
+    auto fetch_corner = [&](auto fast_tag, int row, unsigned ebank, unsigned e2bank, int slot) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        if (HASB) {
+            const char* g = pc;
+            if (!FAST && row > Ny) g = (const char*)(a.B + (size_t)Ny * Bp + ic);
+            pc += (long long)Bp * 4;
+            cp_async8(smE + ebank + slot * E_SLOT, g);
+            cp_async4(smE2 + e2bank + slot * E2_SLOT, g + 8);
+        }
+    };
+    fetch_row(std::false_type{}, ja + 2, 0u, 2);
+    fetch_corner(std::false_type{}, ja + 3, E_BANK, E2_BANK, 0);
+    cp_async_commit();
+    fetch_row(std::false_type{}, ja + 3, UB == 2 ? U_BANK : 0u, 0);
+    fetch_corner(std::false_type{}, ja + 4, E_BANK, E2_BANK, 1);
+    cp_async_commit();
+
     // ---- prologue: state rows ja-2 .. ja+1 and corner rows ja-2 .. ja+2 by direct loads ----
     f2 q[3][3];                                           // q[(j - ja) % 3] = row j of the (rebuilt) state
     f2 dprev[3], Ry0[3], Gl[3], hsy;                      // y state of cell j: q(j+1)-q(j), upper face values, lower flux, hL+hR
@@ -423,67 +487,6 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
         tyj = t0;
         ty2 = t2;
     }
-
-    // ---- fetch of state row r / corner row r into the rings ----
-    // Running byte pointers advance by one row per fetch.  A trip (3 rows) is FAST when every row it fetches is
-    // an interior row (no y-BC remap, no clamping, every row stored); only the last trip(s) of the last chunk
-    // take the generic path.
-    const long long rowB = (long long)Nx * 4, planeB = plane * 4;
-    const long long dOff = (const char*)a.D - (const char*)a.U;
-    const char* pf = (const char*)(a.U + (size_t)(ja + 2) * Nx + xs);     // next state row to fetch
-    const char* pc = (const char*)(a.B + (size_t)(ja + 3) * Bp + ic);     // next corner row to fetch
-    // two rows are in flight at any time (fetch distance 2): per-row BC bookkeeping of the generic path is a 2-deep queue
-    char* ps = (char*)(a.out + (size_t)ja * Nx + i);                      // row j of the output
-    const double* pfac = a.factor + (size_t)ja * Nx + ic;                 // Horton factor plane, row j
-    int ys_next = 0, ys_q = 0;                            // BC source row of the state rows in flight (generic path)
-    bool yflip_next = false, remap_next = false, yflip_q = false, remap_q = false;
-    // ring addressing in bytes: this thread's 8-byte (4-byte for E2) column inside every [.. ][NT] row
-    char* const smb = reinterpret_cast<char*>(&sm);
-    constexpr unsigned U_BANK = 3 * 3 * NT * 8, U_SLOT = 3 * NT * 8, U_VAR = NT * 8;
-    constexpr unsigned D_OFF = offsetof(Rings<STAGE>, D), E_OFF = offsetof(Rings<STAGE>, E), E2_OFF = offsetof(Rings<STAGE>, E2);
-    constexpr unsigned E_BANK = 3 * NT * 8, E_SLOT = NT * 8, E2_BANK = 3 * NT * 4, E2_SLOT = NT * 4;
-    char* const smU = smb + tid * 8;
-    char* const smD = smb + D_OFF + tid * 8;
-    char* const smE = smb + E_OFF + tid * 8;
-    char* const smE2 = smb + E2_OFF + tid * 4;
-    auto fetch_row = [&](auto fast_tag, int row, unsigned ubank, int slot) {
-        constexpr bool FAST = decltype(fast_tag)::value;
-        const char* g = pf;
-        ys_q = ys_next; yflip_q = yflip_next; remap_q = remap_next;      // the row fetched one call ago
-        remap_next = false;
-        yflip_next = false;
-        if (!FAST) {
-            ys_next = row;
-            if (row >= Ny - 2) {                          // uniform
-                const int rr = min(row, Ny - 1);
-                ys_next = row_source(rr, yflip_next);
-                remap_next = ys_next != row;
-                g = (const char*)(a.U + (size_t)ys_next * Nx + xs);
-            }
-        }
-        pf += rowB;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            cp_async8(smU + ubank + slot * U_SLOT + k * U_VAR, g + k * planeB);
-            if (STAGE == 2) cp_async8(smD + slot * U_SLOT + k * U_VAR, g + dOff + k * planeB);
-        }
-    };
-    auto fetch_corner = [&](auto fast_tag, int row, unsigned ebank, unsigned e2bank, int slot) {
-        constexpr bool FAST = decltype(fast_tag)::value;
-        if (HASB) {
-            const char* g = pc;
-            if (!FAST && row > Ny) g = (const char*)(a.B + (size_t)Ny * Bp + ic);
-            pc += (long long)Bp * 4;
-            cp_async8(smE + ebank + slot * E_SLOT, g);
-            cp_async4(smE2 + e2bank + slot * E2_SLOT, g + 8);
-        }
-    };
-    fetch_row(std::false_type{}, ja + 2, 0u, 2);
-    fetch_corner(std::false_type{}, ja + 3, E_BANK, E2_BANK, 0);
-    cp_async_commit();
-    fetch_row(std::false_type{}, ja + 3, UB == 2 ? U_BANK : 0u, 0);
-    fetch_corner(std::false_type{}, ja + 4, E_BANK, E2_BANK, 1);
-    cp_async_commit();
 
     // ---- march: 3 rows per trip; rows beyond jb (last chunk only) are computed on clamped data and not stored ----
     int bank = 0;                                         // (j0 - ja) / 3 mod 2
