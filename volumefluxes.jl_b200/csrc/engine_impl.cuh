@@ -647,8 +647,8 @@ public:
         // the owned boundary rows go to the neighbours first: no consumer reads the x-ghost columns of a halo
         // row from memory (both stage kernels remap them), so the push need not wait for the ghost fill
         if (multi) { push_halo(next, next_index, 2, false); mark("push U"); }
-        const int nthreads = (Ny - 2 * gc) + (Nx - 2 * gc);
-        k_bc_advance<S><<<(nthreads + 127) / 128, 128, 0, stream>>>(next, Nx, Ny, plane, gc, cfg.bc, par.ylo_phys,
+        const long long nthreads = (long long)((Ny - 2 * gc) + (Nx - 2 * gc)) * gc * 6;
+        k_bc_advance<S><<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(next, Nx, Ny, plane, gc, cfg.bc, par.ylo_phys,
                                                                     par.yhi_phys, ctl, advance);
         ++launches;
         mark("bc_advance");

@@ -109,6 +109,16 @@ template <class S>
 __global__ void k_halo_push(const PushArgs<S> a) {
     // blockIdx.y = side * 3 + plane: each (side, plane) is ONE contiguous run of rows*Nx elements on both ends
     // (the gc boundary rows are adjacent in memory), copied with 16-byte peer stores when the runs are aligned.
+    // The strip's CFL maxima are final when this kernel starts (stage 1 is complete): publish them before the
+    // row copies so that the all-gather latency overlaps them on every rank.
+    if (a.with_speed && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < a.nranks) {
+        Mailbox* m = a.mbox[threadIdx.x];
+        const int par = (int)(a.seq & 1ull);
+        m->speed[par][a.rank][0] = a.ctl->maxspeed_bits[0];
+        m->speed[par][a.rank][1] = a.ctl->maxspeed_bits[1];
+        __threadfence_system();
+        *(volatile unsigned long long*)&m->speed_stamp[par][a.rank] = a.seq;
+    }
     const long long per_side = (long long)a.rows * a.Nx;
     if (per_side > 0) {
         const int side = blockIdx.y / 3, k = blockIdx.y - 3 * side;
@@ -144,14 +154,6 @@ __global__ void k_halo_push(const PushArgs<S> a) {
     if (a.rows > 0) {
         if (threadIdx.x == 0 && a.flag_lo) *(volatile unsigned long long*)a.flag_lo = a.stamp;
         if (threadIdx.x == 1 && a.flag_hi) *(volatile unsigned long long*)a.flag_hi = a.stamp;
-    }
-    if (a.with_speed && threadIdx.x < a.nranks) {
-        Mailbox* m = a.mbox[threadIdx.x];
-        const int par = (int)(a.seq & 1ull);
-        m->speed[par][a.rank][0] = a.ctl->maxspeed_bits[0];
-        m->speed[par][a.rank][1] = a.ctl->maxspeed_bits[1];
-        __threadfence_system();
-        *(volatile unsigned long long*)&m->speed_stamp[par][a.rank] = a.seq;
     }
     if (a.dt.enabled) {
         __syncthreads();

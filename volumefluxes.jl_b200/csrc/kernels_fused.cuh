@@ -329,24 +329,27 @@ __global__ void k_update_fe(Par<typename P::C> p, Bathy<P> bt, const typename P:
 template <class S>
 __global__ void k_bc_advance(S* d, int Nx, int Ny, long long plane, int gc, int bc, int ylo_phys, int yhi_phys,
                              Ctl* ctl, int advance) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // one thread per (passive index, ghost layer, side, variable): a single load + store each, so the launch is
+    // a few microseconds although the x ghosts are strided by a whole row
     const int nxp = Ny - 2 * gc;   // passive count for x ghosts
     const int nyp = Nx - 2 * gc;
-    if (t < nxp || (t >= nxp && t < nxp + nyp)) {
-        const int dir = t < nxp ? 0 : 1;
-        const int pp = (dir == 0 ? t : t - nxp) + gc;
+    const int per = gc * 2 * 3;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < (long long)(nxp + nyp) * per) {
+        const int line = (int)(t / per), r = (int)(t - (long long)line * per);
+        const int k = r % 3, side = (r / 3) & 1, g = r / 6;
+        const int dir = line < nxp ? 0 : 1;
+        const int pp = (dir == 0 ? line : line - nxp) + gc;
         const int N = dir == 0 ? Nx : Ny;
         const size_t sa = dir == 0 ? 1 : (size_t)Nx, sp = dir == 0 ? (size_t)Nx : 1;
         const int normal = dir == 0 ? 1 : 2;
-        const bool lo = dir == 0 ? true : (ylo_phys != 0), hi = dir == 0 ? true : (yhi_phys != 0);
-        for (int g = 0; g < gc; ++g) {
-            for (int k = 0; k < 3; ++k) {
-                S* base = d + (size_t)k * plane + (size_t)pp * sp;
-                const S sgn = (bc == SWE_B200_BC_WALL && k == normal) ? (S)-1 : (S)1;
-                bool f;
-                if (lo) base[(size_t)g * sa] = sgn * base[(size_t)bc_source(g, N, gc, bc, true, true, f) * sa];
-                if (hi) base[(size_t)(N - 1 - g) * sa] = sgn * base[(size_t)bc_source(N - 1 - g, N, gc, bc, true, true, f) * sa];
-            }
+        const bool phys = dir == 0 ? true : (side == 0 ? ylo_phys != 0 : yhi_phys != 0);
+        if (phys) {
+            S* base = d + (size_t)k * plane + (size_t)pp * sp;
+            const S sgn = (bc == SWE_B200_BC_WALL && k == normal) ? (S)-1 : (S)1;
+            const int a = side == 0 ? g : N - 1 - g;
+            bool f;
+            base[(size_t)a * sa] = sgn * base[(size_t)bc_source(a, N, gc, bc, true, true, f) * sa];
         }
     }
     if (t == 0 && advance) {
