@@ -280,7 +280,7 @@ def run_ours(args, rank, world):
             traffic = json.loads(tf.read_text()).get(f"k_stage2_{args.dtype}_{n}")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_stage<..., STAGE=2> (K2)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "x2::k_stage_x2<RECON=1, HASB=1, STAGE=2, FRIC=1> (K2: RK2 stage 2, fused)" if args.dtype == "float32" and not args.strict else "k_stage<..., STAGE=2> (K2)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": WORDS_STAGE2 * itemsize * cells_local,
                 "avg_launch_ms": k2_ms, "per": "GPU (rank 0's strip)" if world > 1 else "GPU",
