@@ -134,7 +134,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
-        "data": "synthetic", "config": workload_config(args, n, wet_fraction(case, state)),
+        "data": "synthetic",
+        # same workload as our arm (config 5 at --n); every step of this arm is a bounded sample of it (see `sample`)
+        "config": dict(workload_config(args, args.n, wet_fraction(case, state)), sampled_grid=[n, n]),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -185,8 +187,8 @@ def run_ours(args, rank, world):
                 case, state, y0 = cases.lake_strip_case(n, rank, world, dtype=args.dtype, rows=(offs[rank], sizes[rank]))
                 rows = case["ny"]
     else:
-        case, state = build_case(n, args.dtype)
-        y0, rows = 0, n
+        case, state = build_case(n, args.dtype, ny=args.ny)
+        y0, rows = 0, (args.ny or n)
     wet = wet_fraction(case, state)
     # pinned host buffers for the end-to-end leg
     pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in state]
@@ -232,7 +234,7 @@ def run_ours(args, rank, world):
     tm = sim.run_steps_timed(args.steps)       # CUDA events on the library's stream around the K steps
     barrier()
     clocks = sampler.stop()
-    cells = n * n
+    cells = n * (args.ny or n) if world == 1 else n * n
     sec = max_over_ranks(tm["total_ms"]) * 1e-3
     value = cells * args.steps / sec
 
@@ -341,6 +343,7 @@ def main():
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--ny", type=int, default=None, help="N = 1 only: rows of a non-square grid (strip-shaped tuning runs)")
     ap.add_argument("--equal-strips", action="store_true", dest="equal_strips",
                     help="N > 1: equal-height y-strips instead of the cost-balanced partition")
     ap.add_argument("--dry-cost", type=float, default=0.6, dest="dry_cost",

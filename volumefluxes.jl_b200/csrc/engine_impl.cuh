@@ -212,9 +212,11 @@ public:
         const long long L = (long long)ntiles * c.ny;
         int sizes[4] = {big, 63, 30, 12};
         long long quota[4];
-        quota[3] = std::min(L / 8, W * 2 * sizes[3]);
-        quota[2] = std::min(L / 6, W * 1 * sizes[2]);
-        quota[1] = std::min(L / 4, W * 1 * sizes[1]);
+        double per_warp[4] = {0, 1, 1, 1};          // items of each small class per resident warp
+        if (const char* e = std::getenv("SWE_B200_X2_Q")) sscanf(e, "%lf,%lf,%lf", &per_warp[1], &per_warp[2], &per_warp[3]);
+        quota[3] = std::min(L / 8, (long long)(W * per_warp[3] * sizes[3]));
+        quota[2] = std::min(L / 6, (long long)(W * per_warp[2] * sizes[2]));
+        quota[1] = std::min(L / 4, (long long)(W * per_warp[1] * sizes[1]));
         if (const char* e = std::getenv("SWE_B200_X2_FLAT")) { if (e[0] == '1') quota[1] = quota[2] = quota[3] = 0; }
         quota[0] = L - quota[1] - quota[2] - quota[3];
         // rows of every tile column per class, top of the column = smallest items (any order works: the classes
