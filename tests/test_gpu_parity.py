@@ -439,3 +439,56 @@ def test_large_grid_properties(P, dtype):
     print(f"\n{n}^2 {dtype}: fast-vs-strict {['%.1e' % e for e in err]} strict 1-ulp sensitivity {['%.1e' % e for e in sens]}")
     for e, sn in zip(err, sens):
         assert e <= max(tol, 4 * sn)
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. BASELINE.json's configs at their FULL sizes.  The oracle cannot run these in seconds, so the
+#    strict CUDA path (bit-exact with the oracle at small sizes, section 1) is the reference here:
+#    the fast path must stay within max(tolerance, 4 x the strict path's own 1-ulp sensitivity),
+#    plus size-independent properties (no NaN, non-negative depth, mass budget, BC images).
+# ------------------------------------------------------------------------------------------------
+FULL_CONFIGS = {
+    "config2_swashes_1024_f64": lambda: cases.swashes_dambreak_2d(n=1024, dtype="float64"),
+    "config3_terrain_4096_f32": lambda: cases.terrain_case(n=4096, dtype="float32", level=1.0),
+    "config4_urban_8192_f32": lambda: cases.urban_case(n=8192, dtype="float32", level=1.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_CONFIGS))
+def test_baseline_configs_full_size(P, name):
+    case, st = FULL_CONFIGS[name]()
+    dtype = case["dtype"]
+    N = 10
+    mts = case.get("maximum_timestep")
+
+    def run(state, strict):
+        s = P.simulator_from_case(case, strict=strict)
+        s.set_state_interior(*state)
+        s.run_steps(N, mts)
+        out = np.stack(s.get_state_interior())
+        t = s.t
+        del s
+        return out, t
+
+    fast, t_fast = run(st, False)
+    ref, t_ref = run(st, True)
+    pert, _ = run(cases.perturb_ulp(st, dtype), True)
+    assert np.all(np.isfinite(fast)) and t_fast > 0
+    assert t_fast == pytest.approx(t_ref, rel=1e-5 if dtype == "float32" else 1e-12)
+    sens = cases.field_errors(pert, ref)
+    err = cases.field_errors(fast, ref)
+    tol = F32_TOL if dtype == "float32" else F64_TOL
+    print(f"\n{name}: fast-vs-strict {['%.1e' % e for e in err]} strict 1-ulp sensitivity {['%.1e' % e for e in sens]}")
+    for e, sn in zip(err, sens):
+        assert e <= max(tol, 4 * sn)
+    B = case.get("B")
+    if B is not None and not np.isscalar(B):
+        Bc = cases.synthetic().cell_average(np.asarray(B))[2:-2, 2:-2]
+        h = fast[0].astype(np.float64) - Bc
+        assert h.min() >= -1e-4
+        wet_f = (h >= case["depth_cutoff"])
+        wet_r = (ref[0].astype(np.float64) - Bc) >= case["depth_cutoff"]
+        wet_p = (pert[0].astype(np.float64) - Bc) >= case["depth_cutoff"]
+        assert int(np.sum(wet_f != wet_r)) <= 2 * int(np.sum(wet_p != wet_r)) + 4
+    else:
+        assert fast[0].min() >= -1e-12
