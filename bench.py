@@ -300,7 +300,7 @@ def run_ours(args, rank, world):
         o = oracle.OracleSim(ccase)
         o.set_state_interior(*cstate)
         o.step()
-        csteps = 3
+        csteps = args.cpu_steps      # ~10 s of scalar CPU work at 1024^2 (about 3 M cell-updates/s per core)
         t0 = time.perf_counter()
         for _ in range(csteps):
             o.step()
@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--cpu-n", type=int, default=1024, dest="cpu_n")
+    ap.add_argument("--cpu-steps", type=int, default=30, dest="cpu_steps", help="RK2 steps of the cpu_baseline sample")
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
