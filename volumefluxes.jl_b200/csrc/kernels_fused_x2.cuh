@@ -67,7 +67,7 @@ struct Par2 {
     int rain_kind, infil_kind, infil_first, rows;
     int nitems;                   // work items of one launch (Args2::items)
     float cutoff, kappa, constB;
-    f2 theta, half, mhalf, quarter, g, K /*0.5 rho g*/, i2k, hk, rho, nrdx, nrdy, botx, boty, Cz;
+    f2 theta, hith /*0.5/theta*/, half, mhalf, quarter, g, K /*0.5 rho g*/, i2k, hk, rho, nrdx, nrdy, botx, boty, Cz;
 };
 
 struct Args2 {
@@ -119,6 +119,33 @@ __device__ __forceinline__ void recon2(const Par2& p, const f2 c[3], const f2 bw
         const f2 tf = mul(p.theta, fwd[k]), tb = mul(p.theta, bwd[k]);
         const f2 cen = mul(p.half, add(fwd[k], bwd[k]));
         s[k] = mk(minmod3f(tf.x, cen.x, tb.x), minmod3f(tf.y, cen.y, tb.y));
+    }
+    faces2(p, c, s, tBl, tBr, L, R);
+}
+// X2_TCARRY=1: the y march carries theta * (q(j+1) - q(j)) instead of the raw difference, so the backward limiter
+// argument of cell j+1 is the forward one of cell j (one FMUL2 per variable and row less); the central
+// difference is rebuilt as (0.5/theta) * (tf + tb).
+#ifndef X2_TCARRY
+#define X2_TCARRY 2          // bit 0: stage 1, bit 1: stage 2
+#endif
+#ifndef X2_NOGHOST_FAST
+#define X2_NOGHOST_FAST 0    // 1: warps holding x-ghost pairs never take the FAST trips (which then drop the ghost code)
+#endif
+template <int RECON>
+__device__ __forceinline__ void recon2t(const Par2& p, const f2 c[3], const f2 tb[3], const f2 fwd[3], f2 tBl, f2 tBr,
+                                        f2 Bc, f2 L[3], f2 R[3], f2 tf[3]) {
+    if (RECON == 0) {
+        L[0] = R[0] = sub(c[0], Bc);
+        L[1] = R[1] = c[1];
+        L[2] = R[2] = c[2];
+        return;
+    }
+    f2 s[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        tf[k] = mul(p.theta, fwd[k]);
+        const f2 cen = mul(p.hith, add(tf[k], tb[k]));
+        s[k] = mk(minmod3f(tf[k].x, cen.x, tb[k].x), minmod3f(tf[k].y, cen.y, tb[k].y));
     }
     faces2(p, c, s, tBl, tBr, L, R);
 }
@@ -188,6 +215,9 @@ __device__ __forceinline__ void side2(const Par2& p, f2 h, f2 hu, f2 hv, f2 F[3]
 __device__ __forceinline__ bool any_wet(const Par2& p, f2 hm, f2 hp) {
     return fmaxf(fmaxf(hm.x, hm.y), fmaxf(hp.x, hp.y)) > p.cutoff;
 }
+#ifndef X2_CU12
+#define X2_CU12 1            // bit 0: stage 1, bit 1: stage 2 (measured: helps K1, hurts K2's register allocation)
+#endif
 template <int DIR, bool SPEED>
 __device__ __forceinline__ void cu2(const Par2& p, const f2 Um[3], const f2 Up[3], f2 F[3], f2& speed) {
     f2 Fm[3], Fp[3], epm, enm, epp, enp;
@@ -199,13 +229,24 @@ __device__ __forceinline__ void cu2(const Par2& p, const f2 Um[3], const f2 Up[3
     const bool okx = !(d.x < p.kappa), oky = !(d.y < p.kappa);                            // :67-69
     const f2 r = mk(okx ? rcp_a(d.x) : 0.0f, oky ? rcp_a(d.y) : 0.0f);
     const f2 wp = mul(ap, r), wn = mul(an, r);
-    const f2 c2 = mul(ap, wn);
+    constexpr bool C12 = SPEED ? (X2_CU12 & 1) : ((X2_CU12 >> 1) & 1);      // SPEED <=> stage 1
+    if (C12) {
+        // wp (F- + (-a-)(U- - U+)) + wn F+ : the same flux with the dissipation folded into the left term (12 instead of 13)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const f2 jn = sub(Um[k], Up[k]);
-        f2 t = mul(wp, Fm[k]);
-        t = fma2(wn, Fp[k], t);
-        F[k] = fma2(c2, jn, t);
+        for (int k = 0; k < 3; ++k) {
+            const f2 jn = sub(Um[k], Up[k]);
+            const f2 t = mul(wp, fma2(an, jn, Fm[k]));
+            F[k] = fma2(wn, Fp[k], t);
+        }
+    } else {
+        const f2 c2 = mul(ap, wn);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const f2 jn = sub(Um[k], Up[k]);
+            f2 t = mul(wp, Fm[k]);
+            t = fma2(wn, Fp[k], t);
+            F[k] = fma2(c2, jn, t);
+        }
     }
     if (SPEED) speed = mk(okx ? fmaxf(ap.x, an.x) : 0.0f, oky ? fmaxf(ap.y, an.y) : 0.0f);
     else speed = sp(0.0f);
@@ -215,6 +256,9 @@ __device__ __forceinline__ void cu2(const Par2& p, const f2 Um[3], const f2 Up[3
 // timestepper.jl:41-51): returns the factor the momenta are multiplied by -- 1/(1 - dt*c) of the implicit
 // friction times the wet flag of the dry clean-up -- and raises o0 to the cell bathymetry (for a wet cell
 // o0 - Bc >= cutoff >= 0, so the max is the identity there).
+#ifndef X2_FRIC3
+#define X2_FRIC3 1
+#endif
 template <int FRIC>
 __device__ __forceinline__ f2 tail_factor2(const Par2& p, const f2 prev[3], f2 Bc, f2 czdt, f2& o0) {
     const f2 dpt = sub(o0, Bc);
@@ -224,10 +268,19 @@ __device__ __forceinline__ f2 tail_factor2(const Par2& p, const f2 prev[3], f2 B
         const f2 h = sub(prev[0], Bc);
         const f2 ha = mk(fabsf(h.x), fabsf(h.y));
         const f2 hsa = desing_pos2(p, ha);                       // |h*|; h* = copysign(|h*|, h)
-        const f2 ra = mk(rcp_a(hsa.x), rcp_a(hsa.y));            // 1/|h*|
         // speed = sqrt(u^2+v^2) = sqrt(hu^2+hv^2)/|h*|
         const f2 m2 = fma2(prev[1], prev[1], mul(prev[2], prev[2]));
-        const f2 s = mul(mk(sqrt_a(m2.x), sqrt_a(m2.y)), ra);
+        const f2 sm = mk(sqrt_a(m2.x), sqrt_a(m2.y));
+#if X2_FRIC3
+        if (FRIC == 1) {
+            // friction_bh2021: 1/(1 + dt Cz |m|/h*^3) = h*^3 / (h*^3 + dt Cz |m|): one reciprocal instead of two
+            const f2 h3 = mul(mul(hsa, hsa), hsa);
+            const f2 den = fma2(sm, czdt, h3);
+            return mul(fac, mul(h3, mk(rcp_a(den.x), rcp_a(den.y))));
+        }
+#endif
+        const f2 ra = mk(rcp_a(hsa.x), rcp_a(hsa.y));            // 1/|h*|
+        const f2 s = mul(sm, ra);
         f2 iden;                                                  // 1 / (law denominator), positive for every law
         if (FRIC == 1) iden = mul(ra, ra);                       // h*^2              (friction_bh2021)
         else {
@@ -253,6 +306,18 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// output rows are never read again by the launch that writes them: X2_STCS=1 stores them evict-first (st.global.cs)
+#ifndef X2_STCS
+#define X2_STCS 0
+#endif
+__device__ __forceinline__ void st_out(char* p, f2 v) {
+#if X2_STCS
+    __stcs(reinterpret_cast<float2*>(p), v);
+#else
+    *reinterpret_cast<f2*>(p) = v;
+#endif
+}
 
 constexpr int NT = WPB * 32;
 #ifndef X2_MINB
@@ -340,13 +405,15 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
     };
     // stage 1: q = U^n ; stage 2: q = U^1 = BC(postproc(friction(U^n + dt*dU))) rebuilt on the fly
     const bool xghost = xs != ic;
-    auto finish_row = [&](bool remapped, int ys, bool yflip, const f2 u[3], const f2 d[3], f2 Bc_here, f2 q[3]) {
+    // (a FAST trip -- interior rows of a warp without x-ghost pairs -- has nothing to remap, mirror or flip)
+    auto finish_row = [&](auto fast_tag, bool remapped, int ys, bool yflip, const f2 u[3], const f2 d[3], f2 Bc_here, f2 q[3]) {
+        constexpr bool FASTROW = X2_NOGHOST_FAST && decltype(fast_tag)::value;
         if (STAGE == 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) q[k] = u[k];
         } else {
             f2 Bm = Bc_here;
-            if (HASB && (xghost || remapped)) {          // ghost: bathymetry of the source cells
+            if (!FASTROW && HASB && (xghost || remapped)) {          // ghost: bathymetry of the source cells
                 const float* r0 = a.B + (size_t)ys * Bp + xs;
                 const float m = r0[1] + r0[Bp + 1];
                 Bm = mk(0.25f * (r0[0] + r0[Bp] + m), 0.25f * (m + r0[2] + r0[Bp + 2]));
@@ -356,12 +423,12 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
             const f2 fac = tail_factor2<FRIC>(p, u, Bm, czdt, q[0]);
             q[1] = mul(q[1], fac);
             q[2] = mul(q[2], fac);
-            if (ghost_warp && xswap) {
+            if (!FASTROW && ghost_warp && xswap) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) q[k] = swp(q[k]);
                 q[1] = neg(q[1]);
             }
-            if (yflip) q[2] = neg(q[2]);
+            if (!FASTROW && yflip) q[2] = neg(q[2]);
         }
     };
 
@@ -466,18 +533,29 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
         }
         const f2 tm2 = ty_of(c[0]), tm1 = ty_of(c[1]), t0 = ty_of(c[2]), t1 = ty_of(c[3]), t2 = ty_of(c[4]);
         f2 qa[3], qb[3];
-        finish_row(ys[0] != ja - 2, ys[0], yf[0], u[0], d[0], bcell(tm2, tm1), qa);
-        finish_row(ys[1] != ja - 1, ys[1], yf[1], u[1], d[1], bcell(tm1, t0), qb);
-        finish_row(ys[2] != ja, ys[2], yf[2], u[2], d[2], bcell(t0, t1), q[0]);
-        finish_row(ys[3] != ja + 1, ys[3], yf[3], u[3], d[3], bcell(t1, t2), q[1]);
+        finish_row(std::false_type{}, ys[0] != ja - 2, ys[0], yf[0], u[0], d[0], bcell(tm2, tm1), qa);
+        finish_row(std::false_type{}, ys[1] != ja - 1, ys[1], yf[1], u[1], d[1], bcell(tm1, t0), qb);
+        finish_row(std::false_type{}, ys[2] != ja, ys[2], yf[2], u[2], d[2], bcell(t0, t1), q[0]);
+        finish_row(std::false_type{}, ys[3] != ja + 1, ys[3], yf[3], u[3], d[3], bcell(t1, t2), q[1]);
         f2 b0[3], b1[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             b0[k] = sub(qb[k], qa[k]); b1[k] = sub(q[0][k], qb[k]); dprev[k] = sub(q[1][k], q[0][k]);
         }
         f2 Lt[3], Rp[3], Ly0[3];
-        recon2<RECON>(p, qb, b0, b1, tm1, t0, bcell(tm1, t0), Lt, Rp);              // cell ja-1: upper face only
-        recon2<RECON>(p, q[0], b1, dprev, t0, t1, bcell(t0, t1), Ly0, Ry0);         // cell ja
+        constexpr bool TC = (X2_TCARRY >> (STAGE - 1)) & 1;
+        if (TC) {
+            f2 tb0[3], tb1[3], tfd[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tb0[k] = mul(p.theta, b0[k]);
+            recon2t<RECON>(p, qb, tb0, b1, tm1, t0, bcell(tm1, t0), Lt, Rp, tb1);          // cell ja-1: upper face only
+            recon2t<RECON>(p, q[0], tb1, dprev, t0, t1, bcell(t0, t1), Ly0, Ry0, tfd);     // cell ja
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dprev[k] = RECON ? tfd[k] : dprev[k];              // carried: theta * difference
+        } else {
+            recon2<RECON>(p, qb, b0, b1, tm1, t0, bcell(tm1, t0), Lt, Rp);              // cell ja-1: upper face only
+            recon2<RECON>(p, q[0], b1, dprev, t0, t1, bcell(t0, t1), Ly0, Ry0);         // cell ja
+        }
         f2 s = sp(0.0f);
         Gl[0] = Gl[1] = Gl[2] = sp(0.0f);
         if (__any_sync(0xffffffffu, any_wet(p, Rp[0], Ly0[0]))) cu2<1, STAGE == 1>(p, Rp, Ly0, Gl, s);   // face ja-1/2
@@ -525,10 +603,12 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
             fetch_corner(fast_tag, j + 5, uE[((R + 5) / 3) & 1], uE2[((R + 5) / 3) & 1], (R + 2) % 3);
             cp_async_commit();
             const f2 ty1 = ty_of(E1), ty3 = ty_of(E3);
-            finish_row(remap2, ys2, yflip2, ru, rd, bcell(ty2, ty3), q2);
+            finish_row(fast_tag, remap2, ys2, yflip2, ru, rd, bcell(ty2, ty3), q2);
 
             // ================= reconstruction: row j in x, cell j+1 in y =================
             f2 Lx[3], Rx[3], Ln[3], tBl, tBr, fwd[3], Ly1[3], Ry1[3];
+            constexpr bool TC = (X2_TCARRY >> (STAGE - 1)) & 1;
+            f2 tfw[3];
             {
                 float ql[3], qr[3];
 #pragma unroll
@@ -545,7 +625,8 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
                 for (int k = 0; k < 3; ++k) Ln[k] = mk(Lx[k].y, __shfl_down_sync(0xffffffffu, Lx[k].x, 1));
 #pragma unroll
                 for (int k = 0; k < 3; ++k) fwd[k] = sub(q2[k], q1[k]);
-                recon2<RECON>(p, q1, dprev, fwd, ty1, ty2, bcell(ty1, ty2), Ly1, Ry1);   // cell j+1
+                if (TC) recon2t<RECON>(p, q1, dprev, fwd, ty1, ty2, bcell(ty1, ty2), Ly1, Ry1, tfw);   // cell j+1
+                else recon2<RECON>(p, q1, dprev, fwd, ty1, ty2, bcell(ty1, ty2), Ly1, Ry1);
             }
             // ================= fluxes: faces (i|i+1), (i+1|i+2) of row j and face j+1/2 =================
             // one warp-uniform decision per row: a warp whose x and y faces are all dry skips both evaluations
@@ -583,14 +664,17 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
                 dU[0] = fma2(mk((float)fc.x, (float)fc.y), ninfil, dU[0]);
             }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { dprev[k] = fwd[k]; Ry0[k] = Ry1[k]; Gl[k] = G[k]; }
+            for (int k = 0; k < 3; ++k) {
+                dprev[k] = (TC && RECON) ? tfw[k] : fwd[k];
+                Ry0[k] = Ry1[k]; Gl[k] = G[k];
+            }
             hsy = add(Ly1[0], Ry1[0]);
             // ================= store =================
             const bool st = out_pair && (FAST || j < jb);
             if (STAGE == 1) {
                 if (st) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(ps + k * planeB) = dU[k];
+                    for (int k = 0; k < 3; ++k) st_out(ps + k * planeB, dU[k]);
                 }
             } else {
                 // rungekutta.jl:39-49 stage 2, then friction (prev = U^1) and the dry clean-up
@@ -605,7 +689,7 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
                 o[2] = mul(o[2], fac);
                 if (st) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) *reinterpret_cast<f2*>(ps + k * planeB) = o[k];
+                    for (int k = 0; k < 3; ++k) st_out(ps + k * planeB, o[k]);
                 }
             }
             ps += rowB;
@@ -616,7 +700,7 @@ __global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
         }
     };
     for (int j0 = ja; j0 < jb; j0 += 3, bank ^= 1) {
-        if (j0 + 6 < Ny - 2) trip(std::true_type{}, j0);
+        if (j0 + 6 < Ny - 2 && !(X2_NOGHOST_FAST && ghost_warp)) trip(std::true_type{}, j0);
         else trip(std::false_type{}, j0);
     }
     cp_async_wait_all();                                  // the two rows fetched past the chunk: drain before the rings are reused
