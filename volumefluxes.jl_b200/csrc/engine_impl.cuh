@@ -255,7 +255,7 @@ public:
             a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl; a.items = d_items;
             // persistent warps pulling (tile, rows) items: at most 4 blocks per SM are resident (128 registers)
             const int items = n_items;
-            dim3 g(std::min((items + x2::WPB - 1) / x2::WPB, 148 * X2_MINB));
+            dim3 g(std::min((items + x2::WPB - 1) / x2::WPB, 148 * x2::minb<STAGE>()));
             dim3 b(x2::WPB * 32);
             const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
             const int fr = cfg.friction == SWE_B200_FRICTION_NONE ? 0 : (cfg.friction == SWE_B200_FRICTION_BH2021 ? 1 : 2);

@@ -321,8 +321,13 @@ __device__ __forceinline__ void st_out(char* p, f2 v) {
 
 constexpr int NT = WPB * 32;
 #ifndef X2_MINB
-#define X2_MINB 4
+#define X2_MINB 4            // resident blocks per SM, stage 1 (128 registers)
 #endif
+#ifndef X2_MINB2
+#define X2_MINB2 3           // stage 2 carries more state: 3 blocks x 168 registers (no spills) measured 1.7 % faster than 4 x 128
+#endif
+template <int STAGE>
+constexpr int minb() { return STAGE == 2 ? X2_MINB2 : X2_MINB; }
 
 // Per-thread rings in shared memory.  Every thread only ever reads what it copied itself (its own two
 // columns), so cp.async.wait_group is the only synchronisation: there is no barrier in the kernel.
@@ -341,7 +346,7 @@ struct Rings {
 };
 
 template <int RECON, bool HASB, int STAGE, int FRIC, bool FACTOR>
-__global__ void __launch_bounds__(NT, X2_MINB) k_stage_x2(const Args2 a) {
+__global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
     __shared__ Rings<STAGE> sm;
     constexpr int UB = STAGE == 2 ? 2 : 1;               // banks of the U ring
     const Par2& p = a.p;
