@@ -144,6 +144,18 @@ int swe_b200_enumerate_inner_cells(swe_b200_handle* h, int dir, int ghostcells,
 int swe_b200_enumerate_ghost_cells(swe_b200_handle* h, int dir, int64_t* out /*[n][2]*/,
                                    int64_t* count);
 
+/* ---- device-side reductions for callbacks ---------------------------------------------------------
+ * Callbacks that only need scalars (examples/example_tools.jl:86-90 TotalWaterVolume:
+ * sum(collect(current_interior_state(sim).h) .- B_cell); driven by IntervalWriter, callbacks.jl:40-55)
+ * collect() the whole state in the reference.  This entry reduces over the interior cells of a buffer
+ * on the device and returns 64 bytes:
+ *   out[0] = sum(w - B_cell)   out[1] = sum(hu)   out[2] = sum(hv)   out[3] = max(w - B_cell)
+ *   out[4] = min(w - B_cell)   out[5] = number of wet cells (w - B_cell >= depth_cutoff)
+ *   out[6] = max(|hu|, |hv|)   out[7] = sum(w)
+ * (depths in the storage type like the reference's broadcast, sums accumulated in Float64 in a fixed
+ * order; of THIS handle's strip in a multi-GPU run). */
+int swe_b200_diagnostics(swe_b200_handle* h, int buffer, double out[8]);
+
 /* ---- multi-GPU (y-strips; one process per GPU) -------------------------------------------- */
 /* 128-byte descriptor (CUDA IPC handle + strip layout) of this rank's exchange window: the three
  * state volumes and the mailbox for halo stamps / CFL maxima.  Ranks exchange the descriptors with any

@@ -341,6 +341,44 @@ def test_callback_loop_matches_device_loop(P):
 # 4. boundary conditions and iteration spaces (test_update_bc.jl, test_periodic_bc_2d.jl,
 #    test_for_each_*_2d.jl) through the device kernels
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", ["terrain_shore", "urban_norecon", "swashes_rk2"])
+def test_device_diagnostics_match_host_reduction(P, name, dtype):
+    """swe_b200_diagnostics (device reduction for TotalWaterVolume-style callbacks, examples/example_tools.jl:86-90)
+    against the same quantities computed on the host from collect(state)."""
+    case, state = SMALL_CASES[name](dtype)
+    s = P.simulator_from_case(case)
+    s.set_state_interior(*state)
+    s.run_steps(10)
+    d = s.diagnostics()
+    w, hu, hv = s.get_state_interior()
+    B = case.get("B")
+    Bc = cases.synthetic().cell_average(np.asarray(B))[2:-2, 2:-2].astype(dtype) if B is not None else np.zeros_like(w)
+    h = (w - Bc).astype(np.float64)                  # depths in the storage type, like the reference's broadcast
+    rel = 1e-13
+    assert d["sum_h"] == pytest.approx(h.sum(), rel=rel, abs=1e-300)
+    assert d["sum_w"] == pytest.approx(w.astype(np.float64).sum(), rel=rel)
+    assert d["sum_hu"] == pytest.approx(hu.astype(np.float64).sum(), rel=1e-9, abs=1e-12 * np.abs(hu).sum())
+    assert d["sum_hv"] == pytest.approx(hv.astype(np.float64).sum(), rel=1e-9, abs=1e-12 * np.abs(hv).sum())
+    assert d["max_h"] == h.max() and d["min_h"] == h.min()
+    assert d["wet_cells"] == int((h >= case["depth_cutoff"]).sum())
+    assert d["max_momentum"] == max(np.abs(hu).max(), np.abs(hv).max())
+    assert s.diagnostics() == d                      # fixed reduction order: repeatable bit for bit
+
+
+def test_total_water_volume_callback(P):
+    """IntervalWriter + TotalWaterVolume (callbacks.jl:40-55, examples/example_tools.jl:62-90): constant rain on a
+    closed flat basin raises the volume by rain * area * t."""
+    case, st = cases.rain_case(16, 0.01)
+    s = P.simulator_from_case(case)
+    s.set_state_interior(*st)
+    twv = P.TotalWaterVolume()
+    P.simulate_to_time(s, 2 * 3600.0, callback=P.IntervalWriter(600.0, twv))
+    assert len(twv.times) >= 2 and twv.times == sorted(twv.times)
+    for t, v in zip(twv.times, twv.water_volume):
+        assert v == pytest.approx(16 * 16 * (1.0 + 0.01 * t / 3600.0), rel=1e-12)
+
+
 @pytest.mark.parametrize("bc", ["periodic", "wall", "neumann"])
 @pytest.mark.parametrize("gc", [1, 2])
 def test_update_bc_matches_oracle(P, oracle, bc, gc):
@@ -492,3 +530,59 @@ def test_baseline_configs_full_size(P, name):
         assert int(np.sum(wet_f != wet_r)) <= 2 * int(np.sum(wet_p != wet_r)) + 4
     else:
         assert fast[0].min() >= -1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# 1D problems on the B200 backend: a 1D grid runs as a strip of identical rows of the
+# 2D kernels (the reference itself asserts 1D == x-run of the 2D solver, test_swashes.jl:317-328); the
+# yardstick is the oracle's genuine 1D code path (equations/swe_1D*.jl, 1D grid/BC/friction).
+# ------------------------------------------------------------------------------------------------
+def _run_1d(P, oracle, case, state, T, strict):
+    s = P.simulator_from_case(case, strict=strict)
+    o = oracle.OracleSim(case)
+    s.set_state_interior(*state)
+    o.set_state_interior(*state)
+    ns = P.simulate_to_time(s, T)
+    no = o.simulate_to_time(T)
+    return s, o, ns, no
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_1d_config1_example(P, oracle, strict):
+    """BASELINE configs[0]: examples/shallow_water_1d.jl:31-66,102 (ShallowWaterEquations1DPure, minmod 1.05,
+    RK2, cfl .25, T = 0.05, periodic) on the CUDA path."""
+    case, st = cases.gaussian_1d(pure=True, stepper="rk2", cfl=0.25, theta=1.05)
+    s, o, ns, no = _run_1d(P, oracle, case, st, 0.05, strict)
+    assert ns == no and s.t == o.t == 0.05
+    h, hu = s.get_state_interior()
+    ho, huo = o.get_state_interior()
+    tol = 1e-14 if strict else F64_TOL
+    assert cases.rel_linf(h, ho) <= tol and np.max(np.abs(hu - huo)) <= tol * max(np.max(np.abs(huo)), 1.0)
+    assert abs(h.sum() - st[0].sum()) < 1e-10 * st[0].sum()
+    d = s.diagnostics()
+    assert d["sum_w"] == pytest.approx(h.sum(), rel=1e-13)
+
+
+@pytest.mark.parametrize("friction,stepper", [(None, "fe"), ("bh2021", "rk2")])
+def test_1d_practical_with_bathymetry(P, oracle, friction, stepper):
+    """test_swe1D_sim.jl:95-120 / test_friction_1d.jl:90-115 set-ups (ShallowWaterEquations1D over a
+    BottomTopography1D with the bottom source term, optional implicit friction) against the 1D oracle."""
+    B = 1.0 + 0.05 * np.sin(np.linspace(0.0, 4 * np.pi, 1024 + 5))
+    case, st = cases.gaussian_1d(pure=False, B=B, elevate=1.0, bottom_source=True, stepper=stepper, friction=friction)
+    s, o, ns, no = _run_1d(P, oracle, case, st, 0.05, True)
+    assert ns == no
+    h, hu = s.get_state_interior()
+    ho, huo = o.get_state_interior()
+    assert cases.rel_linf(h, ho) <= 1e-13 and np.max(np.abs(hu - huo)) <= 1e-13 * max(np.max(np.abs(huo)), 1.0)
+    assert s.t == pytest.approx(o.t, rel=1e-14)
+
+
+def test_1d_swashes_wall(P, oracle):
+    """test_swashes.jl:223-258, 1D run of the 4.1.2 dry-bed dam break (WallBC, wet/dry front)."""
+    case, st = cases.swashes41x("412", nx=256, layout="1d", stepper="rk2")
+    s, o, ns, no = _run_1d(P, oracle, case, st, 2.0, True)
+    assert ns == no
+    h, hu = s.get_state_interior()
+    ho, huo = o.get_state_interior()
+    assert cases.rel_linf(h, ho) <= 1e-13 and cases.rel_linf(hu, huo) <= 1e-12
+    assert np.array_equal(h >= case["depth_cutoff"], ho >= case["depth_cutoff"])

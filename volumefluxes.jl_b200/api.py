@@ -45,7 +45,8 @@ __all__ = [
     "current_interior_state", "current_state", "current_time", "current_timestep", "perform_step",
     "simulate_to_time", "update_bc", "for_each_cell", "for_each_inner_cell", "for_each_ghost_cell",
     "cell_faces", "cell_centers", "compute_dx", "compute_dy", "inner_cells", "interior_size",
-    "simulator_from_case", "IntervalWriter",
+    "simulator_from_case", "IntervalWriter", "TotalWaterVolume", "BottomTopography1D",
+    "ShallowWaterEquations1D", "ShallowWaterEquations1DPure",
 ]
 
 XDIR, YDIR = 0, 1
@@ -86,10 +87,20 @@ class NeumannBC:
 
 
 class CartesianGrid:
-    """CartesianGrid(nx, ny; gc=1, boundary=PeriodicBC(), extent=[0 1; 0 1]) (grid.jl:82-90)."""
+    """CartesianGrid(nx, ny; gc=1, boundary=PeriodicBC(), extent=[0 1; 0 1]) (grid.jl:82-90) or the 1D
+    CartesianGrid(nx; gc=1, boundary=PeriodicBC(), extent=[0 1]) (grid.jl:72-80)."""
 
-    def __init__(self, nx: int, ny: int, gc: int = 1, boundary=None, extent=None):
+    def __init__(self, nx: int, ny: Optional[int] = None, gc: int = 1, boundary=None, extent=None):
         self.boundary = boundary if boundary is not None else PeriodicBC()
+        self.dim = 1 if ny is None else 2
+        if ny is None:
+            ext = np.asarray(extent if extent is not None else [0.0, 1.0], dtype=np.float64).reshape(2)
+            self.extent = (float(ext[0]), float(ext[1]))
+            self.ghostcells = (int(gc),)
+            self.totalcells = (int(nx) + 2 * gc,)
+            self.delta = ((ext[1] - ext[0]) / nx,)
+            self.nx, self.ny, self.gc = int(nx), None, int(gc)
+            return
         ext = np.asarray(extent if extent is not None else [[0.0, 1.0], [0.0, 1.0]], dtype=np.float64).reshape(2, 2)
         self.extent = (float(ext[0, 0]), float(ext[0, 1]), float(ext[1, 0]), float(ext[1, 1]))
         self.ghostcells = (int(gc), int(gc))
@@ -189,6 +200,17 @@ class BottomTopography2D:
         self.B = np.ascontiguousarray(B, dtype=backend.realtype)
 
 
+class BottomTopography1D:
+    """Face values, shape (Nx+1,) (bottom_topography.jl:29-37)."""
+
+    def __init__(self, B, backend, grid):
+        B = np.asarray(B)
+        want = (grid.totalcells[0] + 1,)
+        if B.shape != want:   # validate_bottom_topography :78-82
+            raise DomainError(f"Bottom topography should be of size {want} but got {B.shape}")
+        self.B = np.ascontiguousarray(B, dtype=backend.realtype)
+
+
 def is_zero(B) -> bool:
     return bool(np.all(np.asarray(B.B) == 0.0))
 
@@ -212,6 +234,39 @@ class ShallowWaterEquationsPure:
         self.rho, self.g = float(rho), float(g)
         self.B = ConstantBottomTopography()
         self.depth_cutoff = self.desingularizing_kappa = 1e-5
+
+
+class ShallowWaterEquations1D(ShallowWaterEquations):
+    """equations/swe_1D.jl:22-29 -- on this backend a 1D problem runs as a strip of identical rows of the 2D
+    kernels (the reference asserts 1D run == x-run of the 2D solver bitwise, test_swashes.jl:317-328)."""
+
+
+class ShallowWaterEquations1DPure(ShallowWaterEquationsPure):
+    """equations/swe_1D_pure.jl:22-26"""
+
+
+# 1D problems on the 2D kernels: ROWS_1D identical rows, y extent so large that dy / max|lambda_y| never limits dt
+ROWS_1D = 2
+DY_1D = 1.0e30
+
+
+def _embed_1d(backend, system, grid):
+    """(grid, system) of a 1D problem -> the equivalent strip of ROWS_1D identical rows: the y fluxes through the
+    faces of identical rows cancel exactly, hv stays 0, and dt = cfl * min(dx/ax, dy/ay) = cfl * dx/ax."""
+    g2 = CartesianGrid(grid.nx, ROWS_1D, gc=grid.gc, boundary=grid.boundary,
+                       extent=[[grid.extent[0], grid.extent[1]], [0.0, ROWS_1D * DY_1D]])
+    eq = system.equation
+    if eq.pure:
+        eq2 = ShallowWaterEquationsPure(eq.rho, eq.g)
+    else:
+        B = eq.B
+        if isinstance(B, BottomTopography1D):
+            B = BottomTopography2D(np.tile(B.B[None, :], (g2.totalcells[1] + 1, 1)), backend, g2)
+        eq2 = ShallowWaterEquations(B, rho=eq.rho, g=eq.g, depth_cutoff=eq.depth_cutoff,
+                                    desingularizing_kappa=eq.desingularizing_kappa)
+    s2 = ConservedSystem(backend, system.reconstruction, CentralUpwind(eq2), eq2, g2, system.source_terms,
+                         system.implicit_source_term)
+    return s2, g2
 
 
 class LinearReconstruction:
@@ -321,11 +376,11 @@ class _InteriorState:
     """current_interior_state(sim): .h/.hu/.hv numpy views of a host copy (interior_volume_variable.jl:168-176).
     Note: `.h` stores w = h + B for bathymetry-carrying equations, exactly like the reference."""
 
-    def __init__(self, w, hu, hv):
+    def __init__(self, w, hu, hv=None):
         self.h, self.hu, self.hv = w, hu, hv
 
     def __iter__(self):
-        return iter((self.h, self.hu, self.hv))
+        return iter((self.h, self.hu) if self.hv is None else (self.h, self.hu, self.hv))
 
 
 def _ptr(a):
@@ -338,6 +393,11 @@ class Simulator:
 
     def __init__(self, backend, system, timestepper, grid, cfl=0.25, t0=0.0,
                  rank: int = 0, nranks: int = 1, global_ny: Optional[int] = None, y_offset: int = 0):
+        self.dim = getattr(grid, "dim", 2)
+        self.grid_1d = None
+        if self.dim == 1:
+            self.grid_1d = grid
+            system, grid = _embed_1d(backend, system, grid)
         self.backend, self.system, self.timestepper, self.grid = backend, system, timestepper, grid
         eq = system.equation
         L = _lib.lib()
@@ -429,7 +489,10 @@ class Simulator:
             pass
 
     # -- state -------------------------------------------------------------------------------------
-    def set_state_interior(self, w, hu, hv):
+    def set_state_interior(self, w, hu, hv=None):
+        if self.dim == 1:          # (h, hu) of the 1D problem -> identical rows, hv = 0
+            w, hu = (np.tile(np.asarray(a).reshape(1, -1), (ROWS_1D, 1)) for a in (w, hu))
+            hv = np.zeros_like(w)
         arrs = [np.ascontiguousarray(a, dtype=self.dtype) for a in (w, hu, hv)]
         for a in arrs:
             if a.shape != (self.grid.ny, self.grid.nx):
@@ -439,6 +502,8 @@ class Simulator:
     def get_state_interior(self):
         out = [np.empty((self.grid.ny, self.grid.nx), dtype=self.dtype) for _ in range(3)]
         self._check(_lib.lib().swe_b200_get_state_interior(self._h, *[_ptr(a) for a in out]))
+        if self.dim == 1:
+            return [out[0][0].copy(), out[1][0].copy()]
         return out
 
     def get_state_full(self, buffer=0):
@@ -512,6 +577,21 @@ class Simulator:
         self._check(_lib.lib().swe_b200_get_wavespeeds(self._h, _ptr(w)))
         return w
 
+    DIAG_FIELDS = ("sum_h", "sum_hu", "sum_hv", "max_h", "min_h", "wet_cells", "max_momentum", "sum_w")
+
+    def diagnostics(self, buffer=0) -> dict:
+        """Scalar reductions over the interior cells, computed on the device (64 bytes come back instead of
+        collect(state)): what TotalWaterVolume-style callbacks need (examples/example_tools.jl:86-90)."""
+        out = (C.c_double * 8)()
+        self._check(_lib.lib().swe_b200_diagnostics(self._h, buffer, out))
+        d = dict(zip(self.DIAG_FIELDS, [float(v) for v in out]))
+        d["wet_cells"] = int(d["wet_cells"])
+        if self.dim == 1:          # a strip of ROWS_1D identical rows stands for the 1D domain
+            for k in ("sum_h", "sum_hu", "sum_hv", "sum_w"):
+                d[k] /= ROWS_1D
+            d["wet_cells"] //= ROWS_1D
+        return d
+
     def implicit_substep(self, out_buffer, prev_buffer, dt):
         self._check(_lib.lib().swe_b200_implicit_substep(self._h, out_buffer, prev_buffer, float(dt)))
 
@@ -540,8 +620,7 @@ class Simulator:
 
 def set_current_state(simulator: Simulator, new_state):
     """set_current_state!(sim, state) (simulator.jl:119-139): interior values, then update_bc!."""
-    w, hu, hv = new_state
-    simulator.set_state_interior(w, hu, hv)
+    simulator.set_state_interior(*new_state)
 
 
 def current_interior_state(simulator: Simulator) -> _InteriorState:
@@ -608,6 +687,20 @@ class IntervalWriter:
             self.current_t += self.step
 
 
+class TotalWaterVolume:
+    """examples/example_tools.jl:62-90: callback recording sum(w - B_cell) over the interior at every call.
+    The reference collects the whole state to the host; here the sum is a device reduction
+    (swe_b200_diagnostics).  `reduce` combines the per-strip sums of a multi-GPU run (e.g. an all-reduce)."""
+
+    def __init__(self, reduce: Optional[Callable] = None):
+        self.times, self.water_volume, self.reduce = [], [], reduce
+
+    def __call__(self, t, simulator):
+        v = simulator.diagnostics()["sum_h"]
+        self.water_volume.append(self.reduce(v) if self.reduce else v)
+        self.times.append(t)
+
+
 # ---- the backend kernel surface ---------------------------------------------------------------------
 def _grid_probe(backend, grid) -> Simulator:
     eq = ShallowWaterEquationsPure()
@@ -642,26 +735,30 @@ _BC = {"periodic": PeriodicBC, "wall": WallBC, "neumann": NeumannBC}
 
 def simulator_from_case(case: dict, strict: bool = False, fused: bool = True, device: int = 0,
                         rank: int = 0, nranks: int = 1, global_ny=None, y_offset: int = 0) -> Simulator:
-    if case.get("dim", 2) != 2:
-        raise B200Error("the B200 backend covers the 2D step")
+    dim = case.get("dim", 2)
     dtype = np.dtype(case.get("dtype", "float64"))
     backend = make_b200_backend(dtype.type, strict=strict, fused=fused, device=device)
-    ext = case.get("extent", [0.0, 1.0, 0.0, 1.0])
-    grid = CartesianGrid(case["nx"], case["ny"], gc=case.get("gc", 2), boundary=_BC[case.get("bc", "periodic")](),
-                         extent=[[ext[0], ext[1]], [ext[2], ext[3]]])
+    if dim == 1:
+        ext = case.get("extent", [0.0, 1.0])
+        grid = CartesianGrid(case["nx"], gc=case.get("gc", 2), boundary=_BC[case.get("bc", "periodic")](),
+                             extent=[ext[0], ext[1]])
+    else:
+        ext = case.get("extent", [0.0, 1.0, 0.0, 1.0])
+        grid = CartesianGrid(case["nx"], case["ny"], gc=case.get("gc", 2), boundary=_BC[case.get("bc", "periodic")](),
+                             extent=[[ext[0], ext[1]], [ext[2], ext[3]]])
     B = case.get("B")
     if case.get("pure", False):
-        eq = ShallowWaterEquationsPure(case.get("rho", 1.0), case.get("g", 9.81))
+        eq = (ShallowWaterEquations1DPure if dim == 1 else ShallowWaterEquationsPure)(case.get("rho", 1.0), case.get("g", 9.81))
     else:
         if B is None:
             bt = ConstantBottomTopography()
         elif np.isscalar(B):
             bt = ConstantBottomTopography(B)
         else:
-            bt = BottomTopography2D(B, backend, grid)
-        eq = ShallowWaterEquations(bt, rho=case.get("rho", 1.0), g=case.get("g", 9.81),
-                                   depth_cutoff=case.get("depth_cutoff", 1e-5),
-                                   desingularizing_kappa=case.get("kappa", 1e-5))
+            bt = (BottomTopography1D if dim == 1 else BottomTopography2D)(B, backend, grid)
+        eq = (ShallowWaterEquations1D if dim == 1 else ShallowWaterEquations)(
+            bt, rho=case.get("rho", 1.0), g=case.get("g", 9.81), depth_cutoff=case.get("depth_cutoff", 1e-5),
+            desingularizing_kappa=case.get("kappa", 1e-5))
     rec = LinearReconstruction(case.get("theta", 1.2)) if case.get("recon", "linear") == "linear" else NoReconstruction()
     sources = []
     rain, infil = case.get("rain"), case.get("infiltration")

@@ -83,6 +83,7 @@ int swe_b200_reconstruct(swe_b200_handle* h, int dir, int b) { FWD(reconstruct(d
 int swe_b200_get_faces(swe_b200_handle* h, void* l, void* r) { FWD(get_faces(l, r)); }
 int swe_b200_add_time_derivative(swe_b200_handle* h, int ib, int ob, double t, double ms[2]) { FWD(add_time_derivative(ib, ob, t, ms)); }
 int swe_b200_get_wavespeeds(swe_b200_handle* h, void* w) { FWD(get_wavespeeds(w)); }
+int swe_b200_diagnostics(swe_b200_handle* h, int b, double out[8]) { FWD(diagnostics(b, out)); }
 int swe_b200_implicit_substep(swe_b200_handle* h, int ob, int pb, double dt) { FWD(implicit_substep(ob, pb, dt)); }
 int swe_b200_post_proc_substep(swe_b200_handle* h, int b) { FWD(post_proc_substep(b)); }
 int swe_b200_enumerate_cells(swe_b200_handle* h, int64_t* out, int64_t* n) { FWD(enumerate(0, 0, 0, out, n)); }

@@ -168,7 +168,7 @@ public:
         for (int r = 0; r < MAX_RANKS; ++r)
             if (peer_ipc[r] && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
         cudaFree(slab);
-        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl); cudaFree(d_items);
+        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl); cudaFree(d_items); cudaFree(diag_buf);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (auto e : ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -445,6 +445,19 @@ public:
         SWE_CUDA(cudaMemcpyAsync(w, ws, sizeof(S) * plane, cudaMemcpyDeviceToHost, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
         return SWE_B200_OK;
+    }
+    // scalar reductions over the interior of a buffer (TotalWaterVolume-style callbacks): 64 bytes come back
+    double* diag_buf = nullptr;
+    int diagnostics(int b, double out[8]) override {
+        if (bad_buffer(b)) return SWE_B200_EINVAL;
+        const int nb = 148 * 4;
+        if (!diag_buf) SWE_CUDA(cudaMalloc(&diag_buf, sizeof(double) * DIAG_SLOTS * (nb + 1)));
+        k_diag_partial<P><<<nb, 256, 0, stream>>>(vol[cur[b]], bathy(), cfg.nx, cfg.ny, Nx, gc, plane, cfg.depth_cutoff, diag_buf);
+        k_diag_final<<<1, 256, 0, stream>>>(diag_buf, nb, diag_buf + (size_t)nb * DIAG_SLOTS);
+        launches += 2;
+        SWE_CUDA(cudaMemcpyAsync(out, diag_buf + (size_t)nb * DIAG_SLOTS, sizeof(double) * DIAG_SLOTS, cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        return check();
     }
     // system.jl:62-75 on device buffers; the per-direction max lands in ctl->maxspeed_bits
     void launch_time_derivative(S* out, const S* state) {

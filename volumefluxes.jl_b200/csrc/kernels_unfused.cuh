@@ -351,6 +351,61 @@ __global__ void k_pack_interior(S* vol, S* in, int nx, int ny, int Nx, int gc, l
     }
 }
 
+// ---- device-side reductions for callbacks that only need scalars (examples/example_tools.jl:86-90,
+// TotalWaterVolume: sum(collect(state.h) .- B_cell) over the interior; callbacks.jl:40-55): two passes, every
+// partial in double and combined in a fixed order, so the result does not depend on the block schedule.
+// slots: 0 sum(w - B_cell), 1 sum(hu), 2 sum(hv), 3 max(w - B_cell), 4 min(w - B_cell), 5 #wet cells
+// (w - B_cell >= depth_cutoff), 6 max(|hu|, |hv|), 7 sum(w)
+constexpr int DIAG_SLOTS = 8;
+__device__ __forceinline__ void diag_combine(double a[DIAG_SLOTS], const double b[DIAG_SLOTS]) {
+    a[0] += b[0]; a[1] += b[1]; a[2] += b[2];
+    a[3] = fmax(a[3], b[3]); a[4] = fmin(a[4], b[4]);
+    a[5] += b[5]; a[6] = fmax(a[6], b[6]); a[7] += b[7];
+}
+__device__ __forceinline__ void diag_identity(double a[DIAG_SLOTS]) {
+    a[0] = a[1] = a[2] = a[5] = a[7] = 0.0;
+    a[3] = -INFINITY; a[4] = INFINITY; a[6] = 0.0;
+}
+__device__ __forceinline__ void diag_block_reduce(double v[DIAG_SLOTS], double* out) {
+    __shared__ double sh[8][DIAG_SLOTS];
+    for (int o = 16; o > 0; o >>= 1) {
+        double w[DIAG_SLOTS];
+        for (int s = 0; s < DIAG_SLOTS; ++s) w[s] = __shfl_down_sync(0xffffffffu, v[s], o);
+        diag_combine(v, w);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) for (int s = 0; s < DIAG_SLOTS; ++s) sh[warp][s] = v[s];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) diag_combine(v, sh[w]);
+        for (int s = 0; s < DIAG_SLOTS; ++s) out[s] = v[s];
+    }
+}
+template <class P>
+__global__ void __launch_bounds__(256) k_diag_partial(const typename P::S* vol, Bathy<P> bt, int nx, int ny, int Nx,
+                                                      int gc, long long plane, double cutoff, double* partial) {
+    using S = typename P::S;
+    double v[DIAG_SLOTS];
+    diag_identity(v);
+    const long long n = (long long)nx * ny;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q % nx) + gc, j = (int)(q / nx) + gc;
+        const size_t at = (size_t)j * Nx + i;
+        const S w = vol[at], hu = vol[at + plane], hv = vol[at + 2 * plane];
+        const S h = w - (S)bt.cell(i, j);            // in the storage type, like collect(state.h) .- bottom_avg
+        double c[DIAG_SLOTS] = {(double)h, (double)hu, (double)hv, (double)h, (double)h, (double)h >= cutoff ? 1.0 : 0.0,
+                                fmax(fabs((double)hu), fabs((double)hv)), (double)w};
+        diag_combine(v, c);
+    }
+    diag_block_reduce(v, partial + (size_t)blockIdx.x * DIAG_SLOTS);
+}
+static __global__ void __launch_bounds__(256) k_diag_final(const double* partial, int nblocks, double* out) {
+    double v[DIAG_SLOTS];
+    diag_identity(v);
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) diag_combine(v, partial + (size_t)b * DIAG_SLOTS);
+    diag_block_reduce(v, out);
+}
+
 // ---- iteration spaces of the backend kernel surface (kernel_abstractions.jl:66-131, grid.jl:213-253) ------
 // kind 0: for_each_cell, 1: for_each_inner_cell(dir; ghostcells), 2: for_each_ghost_cell(dir).
 // Each work-item records the 1-based indices it would hand to the closure.
