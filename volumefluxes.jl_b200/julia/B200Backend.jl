@@ -164,6 +164,16 @@ function add_time_derivative!(sim::B200Simulator, in_buffer::Integer, out_buffer
     return ms
 end
 
+# ---- scalar reductions for callbacks (examples/example_tools.jl:62-90 TotalWaterVolume collects the whole state;
+# here sum(w - B_cell) etc. are reduced on the device and 64 bytes come back) ------------------------------------
+function diagnostics(sim::B200Simulator, buffer::Integer=0)
+    out = zeros(Float64, 8)
+    check(ccall((:swe_b200_diagnostics, libswe), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), sim.handle, buffer, out), sim.handle)
+    return (sum_h=out[1], sum_hu=out[2], sum_hv=out[3], max_h=out[4], min_h=out[5], wet_cells=Int(out[6]),
+            max_momentum=out[7], sum_w=out[8])
+end
+total_water_volume(sim::B200Simulator) = diagnostics(sim).sum_h
+
 # ---- the kernel surface: closures cannot run inside a precompiled kernel, so the iteration space is
 # enumerated on the device and `f` is applied on the host (kernel_abstractions.jl:66-131) ----------------------
 function for_each_inner_cell(f, sim::B200Simulator, direction; ghostcells=sim.grid.ghostcells[direction])
