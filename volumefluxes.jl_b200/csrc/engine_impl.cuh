@@ -168,7 +168,7 @@ public:
         for (int r = 0; r < MAX_RANKS; ++r)
             if (peer_ipc[r] && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
         cudaFree(slab);
-        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl); cudaFree(d_items); cudaFree(diag_buf);
+        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl); cudaFree(d_items[0]); cudaFree(d_items[1]); cudaFree(diag_buf);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (auto e : ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -197,35 +197,51 @@ public:
         q.botx = s2(c.has_bottom_source ? -0.25 * c.g / dx : 0.0); q.boty = s2(c.has_bottom_source ? -0.25 * c.g / dy : 0.0); q.Cz = s2(c.Cz);
         q.rows = 126;
         if (const char* e = std::getenv("SWE_B200_X2_ROWS")) q.rows = std::max(3, atoi(e) / 3 * 3);   // multiple of 3
-        build_items(c, q.rows);
+        build_items(c, q.rows, 1);
+        build_items(c, q.rows, 2);
         x2_ok = true;
     }
     // Guided schedule of the persistent warps: every tile column (60 output columns) is cut into row segments;
     // most rows go into `big`-row items (the 4-row prologue amortises), the rest into three classes of ever
-    // smaller items that are handed out LAST, sized so that each of the 148*4*4 resident warps gets about one
-    // 63-, one 30- and two 12-row items: the launch then ends within about half a small item everywhere.
-    int4* d_items = nullptr;
-    int n_items = 0;
-    void build_items(const swe_b200_config& c, int big) {
+    // smaller items that are handed out LAST, sized so that each of the W resident warps of the stage gets about
+    // one 63-, one 30- and one 12-row item: the launch then ends within about half a small item everywhere.
+    // One table per stage: stage 2 runs 3 blocks per SM, stage 1 runs 4.
+    // (SWE_B200_X2_WAVES=1 selects a variant whose big items come in whole waves of W and whose remainder is split
+    // 1/2, 1/4, 1/4 over the small classes; measured 1-4 % slower on 2048..16384-row grids: more small items.)
+    int4* d_items[2] = {nullptr, nullptr};
+    int n_items[2] = {0, 0};
+    void build_items(const swe_b200_config& c, int big, int stage) {
         const int ntiles = (c.nx + x2::VW - 1) / x2::VW;
-        const long long W = 148LL * X2_MINB * x2::WPB;
+        const long long W = 148LL * (stage == 2 ? x2::minb<2>() : x2::minb<1>()) * x2::WPB;
         const long long L = (long long)ntiles * c.ny;
         int sizes[4] = {big, 63, 30, 12};
         long long quota[4];
-        double per_warp[4] = {0, 1, 1, 1};          // items of each small class per resident warp
+        double per_warp[4] = {0, 1, 1, 1};          // least items of each small class per resident warp
         if (const char* e = std::getenv("SWE_B200_X2_Q")) sscanf(e, "%lf,%lf,%lf", &per_warp[1], &per_warp[2], &per_warp[3]);
-        quota[3] = std::min(L / 8, (long long)(W * per_warp[3] * sizes[3]));
-        quota[2] = std::min(L / 6, (long long)(W * per_warp[2] * sizes[2]));
-        quota[1] = std::min(L / 4, (long long)(W * per_warp[1] * sizes[1]));
-        if (const char* e = std::getenv("SWE_B200_X2_FLAT")) { if (e[0] == '1') quota[1] = quota[2] = quota[3] = 0; }
-        quota[0] = L - quota[1] - quota[2] - quota[3];
+        bool waves = false;
+        if (const char* e = std::getenv("SWE_B200_X2_WAVES")) waves = e[0] != '0';
+        long long reserve = 0;
+        for (int k = 1; k < 4; ++k) reserve += (long long)(W * per_warp[k] * sizes[k]);
+        reserve = std::min(reserve, L / 2);
+        if (waves) {
+            const long long per_wave = W * big;
+            quota[0] = (L - reserve) / per_wave * per_wave;
+            const long long rest = L - quota[0];
+            quota[1] = rest / 2; quota[2] = rest / 4; quota[3] = rest - quota[1] - quota[2];
+        } else {
+            quota[3] = std::min(L / 8, (long long)(W * per_warp[3] * sizes[3]));
+            quota[2] = std::min(L / 6, (long long)(W * per_warp[2] * sizes[2]));
+            quota[1] = std::min(L / 4, (long long)(W * per_warp[1] * sizes[1]));
+            quota[0] = L - quota[1] - quota[2] - quota[3];
+        }
+        if (const char* e = std::getenv("SWE_B200_X2_FLAT")) { if (e[0] == '1') { quota[1] = quota[2] = quota[3] = 0; quota[0] = L; } }
         // rows of every tile column per class, top of the column = smallest items (any order works: the classes
         // are emitted class by class, tile-fastest, so neighbours in x run at about the same time -> L2 reuse)
         std::vector<int4> items;
         std::vector<int> pos(ntiles, 0);
         for (int k = 0; k < 4; ++k) {
-            // per column share of this class, in whole items; the last class takes whatever is left
-            const long long per_col = quota[k] / ntiles / sizes[k] * sizes[k];
+            // per column share of this class, in whole items (big items rounded down: never more than whole waves); the last class takes whatever is left
+            const long long per_col = (quota[k] / ntiles + (waves && k > 0 ? sizes[k] / 2 : 0)) / sizes[k] * sizes[k];
             std::vector<int> lim(ntiles);
             for (int t = 0; t < ntiles; ++t) lim[t] = k == 3 ? c.ny : (int)std::min<long long>(c.ny, pos[t] + per_col);
             bool any = true;
@@ -241,20 +257,21 @@ public:
                 }
             }
         }
-        n_items = (int)items.size();
-        if (d_items) cudaFree(d_items);
-        cudaMalloc(&d_items, sizeof(int4) * items.size());
-        cudaMemcpy(d_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice);
-        par2.nitems = n_items;
+        const int s = stage - 1;
+        n_items[s] = (int)items.size();
+        if (d_items[s]) cudaFree(d_items[s]);
+        cudaMalloc(&d_items[s], sizeof(int4) * items.size());
+        cudaMemcpy(d_items[s], items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice);
     }
 
     template <int STAGE>
     void launch_stage_x2(const S* U, const S* D, S* out) {
         if constexpr (std::is_same<P, Policy<float, float, false>>::value) {
             x2::Args2 a;
-            a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl; a.items = d_items;
+            a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl; a.items = d_items[STAGE - 1];
+            a.p.nitems = n_items[STAGE - 1];
             // persistent warps pulling (tile, rows) items: at most 4 blocks per SM are resident (128 registers)
-            const int items = n_items;
+            const int items = n_items[STAGE - 1];
             dim3 g(std::min((items + x2::WPB - 1) / x2::WPB, 148 * x2::minb<STAGE>()));
             dim3 b(x2::WPB * 32);
             const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
