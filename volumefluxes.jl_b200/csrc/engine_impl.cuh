@@ -350,18 +350,15 @@ public:
         return SWE_B200_OK;
     }
 
-    // staging buffer reuse: left doubles as scratch for interior pack/unpack when present; else temp
+    // interior_volume.jl:177-186 / interior_volume_variable.jl:168-176: the host arrays are dense (nx, ny) planes, the
+    // volume planes are (Nx, Ny) with ghosts: strided 2D copies straight between the caller's buffers and the
+    // volume (no staging allocation, no pack kernel; pinned host buffers move at PCIe speed).
     int set_state_interior(const void* w, const void* hu, const void* hv) override {
-        const size_t n = (size_t)cfg.nx * cfg.ny;
-        S* tmp = nullptr;
-        SWE_CUDA(cudaMallocAsync(&tmp, sizeof(S) * n * 3, stream));
         const void* src[3] = {w, hu, hv};
+        S* U = vol[cur[0]];
         for (int k = 0; k < 3; ++k)
-            SWE_CUDA(cudaMemcpyAsync(tmp + k * n, src[k], sizeof(S) * n, cudaMemcpyHostToDevice, stream));
-        dim3 b(32, 8), g((cfg.nx + 31) / 32, (cfg.ny + 7) / 8);
-        k_pack_interior<S><<<g, b, 0, stream>>>(vol[cur[0]], tmp, cfg.nx, cfg.ny, Nx, gc, plane, 1);
-        ++launches;
-        SWE_CUDA(cudaFreeAsync(tmp, stream));
+            SWE_CUDA(cudaMemcpy2DAsync(U + (size_t)k * plane + (size_t)gc * Nx + gc, sizeof(S) * Nx, src[k], sizeof(S) * cfg.nx,
+                                       sizeof(S) * cfg.nx, cfg.ny, cudaMemcpyHostToDevice, stream));
         int rc = update_bc(0);
         if (rc) return rc;
         if (peers_open) push_halo(vol[cur[0]], cur[0], 2, false);   // collective: every rank sets its state
@@ -369,16 +366,11 @@ public:
         return check();
     }
     int get_state_interior(void* w, void* hu, void* hv) override {
-        const size_t n = (size_t)cfg.nx * cfg.ny;
-        S* tmp = nullptr;
-        SWE_CUDA(cudaMallocAsync(&tmp, sizeof(S) * n * 3, stream));
-        dim3 b(32, 8), g((cfg.nx + 31) / 32, (cfg.ny + 7) / 8);
-        k_pack_interior<S><<<g, b, 0, stream>>>(vol[cur[0]], tmp, cfg.nx, cfg.ny, Nx, gc, plane, 0);
-        ++launches;
         void* dst[3] = {w, hu, hv};
+        const S* U = vol[cur[0]];
         for (int k = 0; k < 3; ++k)
-            SWE_CUDA(cudaMemcpyAsync(dst[k], tmp + k * n, sizeof(S) * n, cudaMemcpyDeviceToHost, stream));
-        SWE_CUDA(cudaFreeAsync(tmp, stream));
+            SWE_CUDA(cudaMemcpy2DAsync(dst[k], sizeof(S) * cfg.nx, U + (size_t)k * plane + (size_t)gc * Nx + gc, sizeof(S) * Nx,
+                                       sizeof(S) * cfg.nx, cfg.ny, cudaMemcpyDeviceToHost, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
         return check();
     }

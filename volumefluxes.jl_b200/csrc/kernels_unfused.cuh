@@ -338,19 +338,6 @@ __global__ void k_bc(S* d, int Nx, int Ny, long long plane, int gc, int bc, int 
     }
 }
 
-// ---- set / get interior (interior_volume.jl:177-186, interior_volume_variable.jl:168-176) ----------------
-template <class S>
-__global__ void k_pack_interior(S* vol, S* in, int nx, int ny, int Nx, int gc, long long plane, int to_volume) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= nx || j >= ny) return;
-    for (int k = 0; k < 3; ++k) {
-        const size_t qv = (size_t)(j + gc) * Nx + (i + gc) + (size_t)k * plane;
-        const size_t qi = (size_t)j * nx + i + (size_t)k * nx * ny;
-        if (to_volume) vol[qv] = in[qi];
-        else in[qi] = vol[qv];
-    }
-}
-
 // ---- device-side reductions for callbacks that only need scalars (examples/example_tools.jl:86-90,
 // TotalWaterVolume: sum(collect(state.h) .- B_cell) over the interior; callbacks.jl:40-55): two passes, every
 // partial in double and combined in a fixed order, so the result does not depend on the block schedule.
