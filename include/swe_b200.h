@@ -41,7 +41,8 @@ enum { SWE_B200_RECON_NONE = 0, SWE_B200_RECON_LINEAR = 1 };  /* reconstruction/
 enum { SWE_B200_FE = 0, SWE_B200_RK2 = 1 };                   /* timestepper/ *.jl */
 enum { SWE_B200_FRICTION_NONE = 0, SWE_B200_FRICTION_BH2021 = 1, SWE_B200_FRICTION_BSA2012 = 2,
        SWE_B200_FRICTION_FCG2016 = 3 };                       /* friction.jl:30-43    */
-enum { SWE_B200_RAIN_NONE = 0, SWE_B200_RAIN_CONSTANT = 1, SWE_B200_RAIN_TIME_DEPENDENT = 2 };
+enum { SWE_B200_RAIN_NONE = 0, SWE_B200_RAIN_CONSTANT = 1, SWE_B200_RAIN_TIME_DEPENDENT = 2,
+       SWE_B200_RAIN_PLANE = 3 /* FunctionalRain: per-cell values, see swe_b200_set_rain_plane */ };
 enum { SWE_B200_INFIL_NONE = 0, SWE_B200_INFIL_CONSTANT = 1, SWE_B200_INFIL_HORTON = 2 };
 
 /* Plain-old-data description of Grid + Equation + Reconstruction + System + Simulator
@@ -94,6 +95,13 @@ int swe_b200_set_bathymetry(swe_b200_handle* h, const void* B, int64_t n_elems);
 /* HortonInfiltration(...; factor) (sourceterms/source_term_infiltration.jl:37-46,61-65):
  * (nx+2gc) x (ny+2gc) doubles. */
 int swe_b200_set_infiltration_factor(swe_b200_handle* h, const double* factor, int64_t n_elems);
+/* FunctionalRain(rain_function, grid) (sourceterms/source_term_rain.jl:57-68): the reference calls an arbitrary
+ * closure rain_function(t, x, y) per cell and adds the result to out.h (:73-75).  A precompiled kernel cannot run
+ * the closure: with cfg.rain_kind = SWE_B200_RAIN_PLANE the host evaluates it at every cell centre
+ * (cell_center, grid.jl:117-121, ALL (nx+2gc) x (ny+2gc) cells like for_each_cell) and hands the values over here --
+ * once for a time-independent function, before every step for a time-dependent one (stream-ordered, may be called
+ * between steps).  Units: what the closure returns (m/s; no /3600).  Zero until first set. */
+int swe_b200_set_rain_plane(swe_b200_handle* h, const double* values, int64_t n_elems);
 
 /* set_current_state! (simulator.jl:119-139): nx x ny per variable, then update_bc!. */
 int swe_b200_set_state_interior(swe_b200_handle* h, const void* w, const void* hu, const void* hv);

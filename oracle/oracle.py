@@ -61,6 +61,7 @@ def lib():
         L.orc_destroy.argtypes = [vp]
         L.orc_set_bathymetry.argtypes = [vp, vp]
         L.orc_set_infiltration_factor.argtypes = [vp, vp]
+        L.orc_set_rain_plane.argtypes = [vp, vp]
         L.orc_set_state_interior.argtypes = [vp, vp, vp, vp]
         L.orc_set_state_full.argtypes = [vp, i32, vp]
         L.orc_get_state_full.argtypes = [vp, i32, vp]
@@ -139,6 +140,8 @@ class OracleSim:
         rain = case.get("rain")
         if rain is None:
             c.rain_kind = 0
+        elif isinstance(rain, dict):      # FunctionalRain(rain_function, grid), source_term_rain.jl:57-68
+            c.rain_kind = 3
         elif np.isscalar(rain):
             c.rain_kind, c.rain_rate = 1, float(rain)
         else:
@@ -182,6 +185,29 @@ class OracleSim:
             f = np.ascontiguousarray(infil["factor"], dtype=np.float64)
             assert f.shape == (self.Ny, self.Nx)
             lib().orc_set_infiltration_factor(self._h, _ptr(f))
+
+        self._rain_fn = rain["function"] if isinstance(rain, dict) else None
+        if self._rain_fn is not None:
+            assert self.dim == 2
+            self._rain_t = None
+            self._refresh_rain(c.t0)
+
+    def _refresh_rain(self, t):
+        """compute_rain(rain::FunctionalRain, t, index) = rain_function(t, cell_center(grid, index)...)
+        (source_term_rain.jl:65-68, grid.jl:117-121), evaluated for every cell like the reference's for_each_cell."""
+        if self._rain_fn is None or t == self._rain_t:
+            return
+        c = self.cfg
+        dx = (c.extent[1] - c.extent[0]) / c.nx
+        dy = (c.extent[3] - c.extent[2]) / c.ny
+        v = np.empty((self.Ny, self.Nx), dtype=np.float64)
+        for j in range(self.Ny):
+            y = c.extent[2] + dy * ((j + 1) - 0.5 - c.gc)
+            for i in range(self.Nx):
+                x = c.extent[0] + dx * ((i + 1) - 0.5 - c.gc)
+                v[j, i] = self._rain_fn(t, x, y)
+        lib().orc_set_rain_plane(self._h, _ptr(v))
+        self._rain_t = t
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -242,9 +268,19 @@ class OracleSim:
         lib().orc_set_time(self._h, float(t), float(dt))
 
     def step(self, max_dt=float("inf"), advance=True):
+        self._refresh_rain(self.t)
         (lib().orc_step_advance if advance else lib().orc_step)(self._h, float(max_dt))
 
     def simulate_to_time(self, T, match_endtime=True, maximum_timestep=None, max_steps=0):
+        if self._rain_fn is not None:      # simulator.jl:179-212 as a host loop: the closure is re-evaluated every step
+            n = 0
+            while self.t < T:
+                max_dt = (T - self.t) if match_endtime else float("inf")
+                if maximum_timestep:
+                    max_dt = min(max_dt, maximum_timestep)
+                self.step(max_dt)
+                n += 1
+            return n
         return lib().orc_simulate_to_time(self._h, float(T), int(match_endtime),
                                           float(maximum_timestep or 0.0), int(max_steps))
 

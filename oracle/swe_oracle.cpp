@@ -39,7 +39,7 @@ struct orc_config {
     int32_t friction;     // 0 none, 1 bh2021, 2 bsa2012, 3 fcg2016
     int32_t has_bathymetry;   // 0: ConstantBottomTopography(const_B), 1: BottomTopography array
     int32_t has_bottom_source;
-    int32_t rain_kind;    // 0 none, 1 ConstantRain, 2 TimeDependentRain
+    int32_t rain_kind;    // 0 none, 1 ConstantRain, 2 TimeDependentRain, 3 FunctionalRain (per-cell values of the closure)
     int32_t infil_kind;   // 0 none, 1 ConstantInfiltration, 2 HortonInfiltration
     int32_t infil_first;  // order of the two per-cell source terms in the source list
     int32_t n_rain;       // TimeDependentRain table length
@@ -96,6 +96,7 @@ struct Oracle {
     std::vector<S> left, right, ws;   // system.jl:40-42
     std::vector<S> B;         // corner / interface bathymetry, (Nx+1)[x(Ny+1)]
     std::vector<double> factor;  // Horton factor (Nx,Ny); Float64 in the reference default ctor
+    std::vector<double> rainp;   // FunctionalRain: rain_function(t, x, y) at every cell centre (source_term_rain.jl:65-68), host-evaluated
     int cur[3];               // rotation of substep_outputs (simulator.jl:175-176)
 
     explicit Oracle(const orc_config& cfg) : c(cfg) {
@@ -114,6 +115,7 @@ struct Oracle {
         ws.assign(plane, (S)0);
         if (c.has_bathymetry) B.assign((Nx + 1) * (c.dim == 1 ? 1 : Ny + 1), (S)0);
         if (c.infil_kind == 2) factor.assign(plane, 1.0);
+        if (c.rain_kind == 3) rainp.assign(plane, 0.0);
     }
     int nsub() const { return c.stepper == 1 ? 2 : 1; }   // rungekutta.jl:24, forwardeuler.jl:26
 
@@ -359,7 +361,10 @@ struct Oracle {
                     out[q] = (S)(out[q] - f);
                 }
             }
-            if (!do_infil && c.rain_kind != 0) {
+            if (!do_infil && c.rain_kind == 3) {        // output_h[index] += rain_function(t, x, y)  (:65-68, 73-75)
+#pragma omp parallel for
+                for (int64_t q = 0; q < plane; ++q) out[q] = (S)(out[q] + rainp[q]);
+            } else if (!do_infil && c.rain_kind != 0) {
                 const double r = rain_rate(tt);
 #pragma omp parallel for
                 for (int64_t q = 0; q < plane; ++q) out[q] = (S)(out[q] + r);
@@ -575,6 +580,13 @@ int orc_set_infiltration_factor(void* hp, const double* f) {
     return dispatch(hp, [&](auto& o) {
         if (o.c.infil_kind != 2) return -1;
         std::copy(f, f + o.plane, o.factor.begin());
+        return 0;
+    });
+}
+int orc_set_rain_plane(void* hp, const double* r) {
+    return dispatch(hp, [&](auto& o) {
+        if (o.c.rain_kind != 3) return -1;
+        std::copy(r, r + o.plane, o.rainp.begin());
         return 0;
     });
 }

@@ -138,6 +138,27 @@ def rain_case(n=10, rain=0.01, dtype="float64"):
     return case, (w, np.zeros_like(w), np.zeros_like(w))
 
 
+# test_rain.jl:99-101, 112-122, 133-140: the closures handed to FunctionalRain
+def constant_rain_function(t, x, y):
+    return 0.01 / 3600.0
+
+
+def timedependent_rain_function(t, x, y):
+    if t < 1 * 3600:
+        rate = 15.0 * 0.001
+    elif t < 2 * 3600:
+        rate = 0.3 * 0.001
+    else:
+        rate = 20.0 * 0.001
+    return rate / 3600
+
+
+def spatial_rain_function(t, x, y):
+    if t > 3600.0 and t < 7200.0:
+        return 3 * (x / 500) * (y / 500) * 0.01 / 3600.0
+    return 0.0
+
+
 def infiltration_case(n=10, dtype="float64", t0=1e6):
     case = dict(dim=2, dtype=dtype, nx=n, ny=n, gc=2, bc="periodic", extent=[0.0, 100.0, 0.0, 100.0],
                 theta=1.2, cfl=0.25, stepper="fe", recon="linear", infiltration={}, t0=t0)

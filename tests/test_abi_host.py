@@ -68,8 +68,12 @@ def test_host_side_validation_needs_no_gpu(pkg):
     P.ConservedSystem(be, P.LinearReconstruction(), P.CentralUpwind(eq), eq, grid, [P.SourceTermBottom()])
     with pytest.raises(P.DomainError):
         P.TimeDependentRain([1.0, 2.0], [0.0])
-    with pytest.raises(P.B200Error):
-        P.FunctionalRain(lambda t, x, y: 0.0, grid)
+    # FunctionalRain: the closure is evaluated on the host (vectorised, or cell by cell when it branches on x / y)
+    fr = P.FunctionalRain(lambda t, x, y: 2.0 * x + y if t > 0 else 0.0, grid)
+    v = fr.values(1.0, np.arange(3.0), np.arange(2.0))
+    assert v.shape == (2, 3) and v[1, 2] == 5.0 and np.all(fr.values(0.0, np.arange(3.0), np.arange(2.0)) == 0.0)
+    assert np.array_equal(P.FunctionalRain(lambda t, x, y: 1.0 if x > 0.5 else 0.0, grid).values(0.0, np.arange(3.0), np.arange(2.0)),
+                          np.array([[0.0, 1.0, 1.0]] * 2))
 
 
 def test_no_cpu_fallback_in_product(pkg):

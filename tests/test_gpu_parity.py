@@ -586,3 +586,58 @@ def test_1d_swashes_wall(P, oracle):
     ho, huo = o.get_state_interior()
     assert cases.rel_linf(h, ho) <= 1e-13 and cases.rel_linf(hu, huo) <= 1e-12
     assert np.array_equal(h >= case["depth_cutoff"], ho >= case["depth_cutoff"])
+
+
+# ------------------------------------------------------------------------------------------------
+# FunctionalRain: the closure is evaluated on the host at every cell centre and uploaded
+# (swe_b200_set_rain_plane); test_rain.jl:98-146 on the CUDA path, and bit-exact against the oracle.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [True, False])
+def test_functional_rain_reference_cases(P, oracle, fused):
+    case, st = cases.rain_case(10, 0.01)
+
+    def run(fn, **kw):
+        s = P.simulator_from_case(dict(case, rain=dict(function=fn, **kw)), strict=True, fused=fused)
+        s.set_state_interior(*st)
+        P.simulate_to_time(s, 3 * 3600.0)
+        assert s.t == pytest.approx(3 * 3600.0, abs=1e-10)
+        return s
+
+    s1 = run(cases.constant_rain_function, time_dependent=False)      # device-resident loop
+    w, hu, hv = s1.get_state_interior()
+    assert np.all(hu == 0.0) and np.all(hv == 0.0)
+    assert w.max() == pytest.approx(1.03, abs=1e-12) and w.min() == pytest.approx(1.03, abs=1e-12)
+    w3 = run(cases.timedependent_rain_function).get_state_interior()[0]
+    assert w3.max() == pytest.approx(1.0353, abs=1e-4) and w3.min() == pytest.approx(1.0353, abs=1e-4)
+    s5 = run(cases.spatial_rain_function)
+    w5 = s5.get_state_interior()[0]
+    assert w5.sum() == pytest.approx(w.sum(), abs=1e-2)
+    o = oracle.OracleSim(dict(case, rain={"function": cases.spatial_rain_function}))
+    o.set_state_interior(*st)
+    o.simulate_to_time(3 * 3600.0)
+    assert s5.t == o.t
+    for a, b in zip(s5.get_state_interior(), o.get_state_interior()):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("strict", [True, False])
+def test_functional_rain_on_terrain(P, oracle, dtype, strict):
+    """spatially varying, time-dependent rain over the config-3 terrain (bottom source, friction, Horton): the
+    generic fused kernels read the uploaded values per cell; strict = bit-exact, fast = within tolerance."""
+    case, st = cases.terrain_case(n=64, dtype=dtype, wavelength=48.0, friction="bh2021", film=0.1)
+    # only exactly rounded operations: the vectorised host evaluation equals the oracle's scalar one bit for bit
+    fn = lambda t, x, y: (1.0 + 0.75 * (x / 64.0) * (1.0 - y / 64.0)) * (2e-4 if t < 0.8 else 5e-5)
+    case = dict(case, rain={"function": fn})
+    s = P.simulator_from_case(case, strict=strict)
+    o = oracle.OracleSim(case)
+    s.set_state_interior(*st)
+    o.set_state_interior(*st)
+    for _ in range(12):
+        s.step(1.0)
+        o.step(1.0)
+    a, b = interior(s.get_state_full()), interior(o.get_state_full())
+    if strict:
+        assert s.t == o.t and np.array_equal(a, b)
+    else:
+        assert max(cases.field_errors(a, b)) <= (F64_TOL if dtype == "float64" else 20 * F32_TOL)

@@ -197,6 +197,28 @@ def test_rain_functions_and_run(O):
     assert w.max() == pytest.approx(0.015 + 1.0, abs=1e-12) and w.min() == pytest.approx(0.015 + 1.0, abs=1e-12)
 
 
+# ---- test_rain.jl:98-146: FunctionalRain (constant / time-dependent / spatial closures) ----------------
+def test_functional_rain(O):
+    case, st = cases.rain_case(10, 0.01)
+
+    def run(fn):
+        s = O.OracleSim(dict(case, rain={"function": fn}))
+        s.set_state_interior(*st)
+        s.simulate_to_time(3 * 3600.0)
+        assert s.t == pytest.approx(3 * 3600.0, abs=1e-10)
+        return s.get_state_interior()
+
+    w, hu, hv = run(cases.constant_rain_function)
+    assert np.all(hu == 0.0) and np.all(hv == 0.0)
+    assert w.max() == pytest.approx(3 * 0.01 + 1.0, abs=1e-12) and w.min() == pytest.approx(3 * 0.01 + 1.0, abs=1e-12)
+    w3, hu, hv = run(cases.timedependent_rain_function)
+    assert np.all(hu == 0.0) and np.all(hv == 0.0)
+    assert w3.max() == pytest.approx(0.0353 + 1.0, abs=1e-4) and w3.min() == pytest.approx(0.0353 + 1.0, abs=1e-4)
+    w5 = run(cases.spatial_rain_function)[0]
+    assert w5.sum() == pytest.approx(w.sum(), abs=1e-2)
+    assert w5.max() - w5.min() > 1e-3          # the rain really varied in space
+
+
 def test_infiltration_functions_and_run(O):
     case, st = cases.infiltration_case()
     s = O.OracleSim(case)

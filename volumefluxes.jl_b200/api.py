@@ -302,9 +302,22 @@ class TimeDependentRain:
 
 
 class FunctionalRain:
-    def __init__(self, *a, **k):
-        raise B200Error("FunctionalRain runs an arbitrary host closure per cell; the precompiled B200 backend "
-                        "does not support it (use ConstantRain / TimeDependentRain)")
+    """FunctionalRain(rain_function, grid) (source_term_rain.jl:57-68): out.h += rain_function(t, x, y) at every cell
+    centre.  A precompiled kernel cannot run the closure, so the host evaluates it over all cell centres
+    (vectorised when the function accepts arrays) and uploads the values (swe_b200_set_rain_plane): once if
+    `time_dependent=False`, before every step otherwise -- the simulation then runs the per-step host loop."""
+
+    def __init__(self, rain_function: Callable, grid=None, time_dependent: bool = True):
+        self.rain_function, self.grid, self.time_dependent = rain_function, grid, bool(time_dependent)
+
+    def values(self, t: float, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+        shape = (y.size, x.size)
+        try:
+            v = np.asarray(self.rain_function(t, x[None, :], y[:, None]), dtype=np.float64)
+            v = np.broadcast_to(v, shape)
+        except Exception:
+            v = np.array([[self.rain_function(t, float(a), float(b)) for a in x] for b in y], dtype=np.float64)
+        return np.ascontiguousarray(v)
 
 
 class HortonInfiltration:
@@ -420,17 +433,20 @@ class Simulator:
         c.has_bathymetry = 1 if (has_B and not zero_B) else 0
         c.const_B = 0.0 if has_B else float(eq.B.B)
         c.has_bottom_source = 1 if any(isinstance(s, SourceTermBottom) for s in system.source_terms) else 0
-        order = [s for s in system.source_terms if isinstance(s, (ConstantRain, TimeDependentRain,
+        order = [s for s in system.source_terms if isinstance(s, (ConstantRain, TimeDependentRain, FunctionalRain,
                                                                   HortonInfiltration, ConstantInfiltration))]
-        rains = [s for s in order if isinstance(s, (ConstantRain, TimeDependentRain))]
+        rains = [s for s in order if isinstance(s, (ConstantRain, TimeDependentRain, FunctionalRain))]
         infils = [s for s in order if isinstance(s, (HortonInfiltration, ConstantInfiltration))]
         if len(rains) > 1 or len(infils) > 1:
             raise B200Error("at most one rain and one infiltration source term are supported")
         self._horton = None
+        self._frain, self._frain_t = None, None
         if rains:
             r = rains[0]
             if isinstance(r, ConstantRain):
                 c.rain_kind, c.rain_rate = 1, r.rain_rate
+            elif isinstance(r, FunctionalRain):
+                c.rain_kind, self._frain = 3, r
             else:
                 if len(r.rain_rates) > 16:
                     raise B200Error("TimeDependentRain table too long (max 16)")
@@ -472,6 +488,13 @@ class Simulator:
         if self._horton is not None:
             f = self._horton.factor
             self._check(L.swe_b200_set_infiltration_factor(self._h, _ptr(f), f.size))
+        if self._frain is not None:      # cell_center of ALL cells, ghosts included (grid.jl:117-121)
+            gc = grid.gc
+            dx = (grid.extent[1] - grid.extent[0]) / grid.nx
+            dy = (grid.extent[3] - grid.extent[2]) / c.global_ny
+            self._frain_x = grid.extent[0] + dx * (np.arange(1, self.Nx + 1) - 0.5 - gc)
+            self._frain_y = grid.extent[2] + dy * (np.arange(1, self.Ny + 1) - 0.5 - gc + y_offset)
+            self._refresh_rain(float(t0))
 
     def _check(self, rc):
         if rc != 0:
@@ -534,10 +557,31 @@ class Simulator:
         self._check(_lib.lib().swe_b200_set_time(self._h, float(t), float(dt)))
 
     # -- stepping ---------------------------------------------------------------------------------------
+    def _refresh_rain(self, t=None):
+        """FunctionalRain: (re-)evaluate the closure at the time of the coming step and upload the values"""
+        if self._frain is None:
+            return
+        t = self.t if t is None else t
+        if self._frain_t is None or (self._frain.time_dependent and t != self._frain_t):
+            v = self._frain.values(t, self._frain_x, self._frain_y)
+            self._check(_lib.lib().swe_b200_set_rain_plane(self._h, _ptr(v), v.size))
+            self._frain_t = t
+
+    @property
+    def host_loop_required(self) -> bool:
+        """a time-dependent FunctionalRain needs the host between steps"""
+        return self._frain is not None and self._frain.time_dependent
+
     def step(self, max_dt=math.inf, advance=True):
+        if self.host_loop_required:
+            self._refresh_rain()
         self._check(_lib.lib().swe_b200_step(self._h, float(max_dt), 1 if advance else 0))
 
     def run_steps(self, n, maximum_timestep=None):
+        if self.host_loop_required:
+            for _ in range(int(n)):
+                self.step(maximum_timestep if maximum_timestep else math.inf)
+            return
         self._check(_lib.lib().swe_b200_run_steps(self._h, int(n), float(maximum_timestep or 0.0)))
 
     def run_steps_timed(self, n, maximum_timestep=None):
@@ -653,6 +697,8 @@ def simulate_to_time(simulator: Simulator, endtime, match_endtime=True, callback
     """simulate_to_time (simulator.jl:179-212).  Without a callback the loop runs device-resident
     (dt and t never visit the host between steps); with one, the reference's per-step host loop is kept."""
     L = _lib.lib()
+    if callback is None and simulator.host_loop_required:
+        callback = lambda t, s: None
     if callback is None:
         n = C.c_int64()
         simulator._check(L.swe_b200_simulate_to_time(simulator._h, float(endtime), 1 if match_endtime else 0,
@@ -768,7 +814,10 @@ def simulator_from_case(case: dict, strict: bool = False, fused: bool = True, de
             grid, backend, factor=infil.get("factor", 1.0), fc=infil.get("fc", 3.272e-5),
             f0=infil.get("f0", 1.977e-4), k=infil.get("k", 2.43e-3))
     if rain is not None:
-        rain_term = ConstantRain(rain) if np.isscalar(rain) else TimeDependentRain(rain[0], rain[1])
+        if isinstance(rain, dict):
+            rain_term = FunctionalRain(rain["function"], grid, time_dependent=rain.get("time_dependent", True))
+        else:
+            rain_term = ConstantRain(rain) if np.isscalar(rain) else TimeDependentRain(rain[0], rain[1])
     pair = [infil_term, rain_term] if case.get("infil_first", True) else [rain_term, infil_term]
     sources += [s for s in pair if s is not None]
     if case.get("bottom_source", False):

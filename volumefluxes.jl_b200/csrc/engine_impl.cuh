@@ -57,6 +57,7 @@ public:
     S *left = nullptr, *right = nullptr, *ws = nullptr;
     S* B = nullptr;
     double* factor = nullptr;
+    double* rainp = nullptr;     // FunctionalRain values per cell (rain_kind == SWE_B200_RAIN_PLANE)
     Ctl* ctl = nullptr;
     Ctl* h_ctl = nullptr;   // pinned mirror
     int cur[3] = {0, 1, 2};
@@ -139,6 +140,10 @@ public:
             SWE_CUDA(cudaMalloc(&B, sizeof(S) * (size_t)Bp * (Ny + 1)));
             SWE_CUDA(cudaMemsetAsync(B, 0, sizeof(S) * (size_t)Bp * (Ny + 1), stream));
         }
+        if (c.rain_kind == SWE_B200_RAIN_PLANE) {
+            SWE_CUDA(cudaMalloc(&rainp, sizeof(double) * plane));
+            SWE_CUDA(cudaMemsetAsync(rainp, 0, sizeof(double) * plane, stream));
+        }
         if (c.infil_kind == SWE_B200_INFIL_HORTON) {
             SWE_CUDA(cudaMalloc(&factor, sizeof(double) * plane));
             std::vector<double> ones((size_t)plane, 1.0);   // HortonInfiltration default factor=1.0
@@ -168,7 +173,7 @@ public:
         for (int r = 0; r < MAX_RANKS; ++r)
             if (peer_ipc[r] && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
         cudaFree(slab);
-        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(ctl); cudaFree(d_items[0]); cudaFree(d_items[1]); cudaFree(diag_buf);
+        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(rainp); cudaFree(ctl); cudaFree(d_items[0]); cudaFree(d_items[1]); cudaFree(diag_buf);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (auto e : ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -182,6 +187,7 @@ public:
         const char* off = std::getenv("SWE_B200_NO_X2");
         if (off && off[0] == '1') return;
         if (!fused_ok || (Nx & 1) || !(c.depth_cutoff >= 0) || !(c.kappa > 0) || !(c.kappa < 1)) return;
+        if (c.rain_kind == SWE_B200_RAIN_PLANE) return;      // per-cell rain: generic fused kernels
         const int gny = c.global_ny > 0 ? c.global_ny : c.ny;
         const double dx = (c.extent[1] - c.extent[0]) / c.nx, dy = (c.extent[3] - c.extent[2]) / gny;
         auto s2 = [](double v) { return make_float2((float)v, (float)v); };
@@ -339,6 +345,16 @@ public:
         SWE_CUDA(cudaStreamSynchronize(stream));
         return SWE_B200_OK;
     }
+    int set_rain_plane(const double* r, int64_t n) override {
+        if (cfg.rain_kind != SWE_B200_RAIN_PLANE) { err = "no FunctionalRain (rain_kind = SWE_B200_RAIN_PLANE) configured"; return SWE_B200_EINVAL; }
+        if (n != plane) {
+            err = "Rain values should be of size (" + std::to_string(Nx) + ", " + std::to_string(Ny) + ")";
+            return SWE_B200_EDOMAIN;
+        }
+        SWE_CUDA(cudaMemcpyAsync(rainp, r, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));     // the caller may reuse its buffer
+        return SWE_B200_OK;
+    }
     int set_infiltration_factor(const double* f, int64_t n) override {
         if (cfg.infil_kind != SWE_B200_INFIL_HORTON) { err = "no HortonInfiltration configured"; return SWE_B200_EINVAL; }
         if (n != plane) {   // validate_infiltration_factor, source_term_infiltration.jl:61-65
@@ -493,7 +509,7 @@ public:
                 ++launches;
             }
             if (!do_infil && cfg.rain_kind != SWE_B200_RAIN_NONE) {
-                k_point_source<P><<<grd1(plane), 256, 0, stream>>>(out, plane, ctl, 0, nullptr);
+                k_point_source<P><<<grd1(plane), 256, 0, stream>>>(out, plane, ctl, 0, rainp);
                 ++launches;
             }
         }
@@ -569,7 +585,7 @@ public:
     template <int STAGE>
     void launch_stage(const S* U, const S* D, S* out) {
         StageArgs<P> a;
-        a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.Bp = Bp; a.factor = factor; a.ctl = ctl;
+        a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.Bp = Bp; a.factor = factor; a.rainp = rainp; a.ctl = ctl;
         a.rain_kind = cfg.rain_kind; a.infil_kind = cfg.infil_kind; a.infil_first = cfg.infil_first;
         a.rows = FUSED_ROWS;
         const int nwarps = (cfg.nx + FUSED_VW - 1) / FUSED_VW;

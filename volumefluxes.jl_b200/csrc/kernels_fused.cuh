@@ -38,6 +38,7 @@ struct StageArgs {
     const S* B;        // corners (pitch Bp) or nullptr
     int Bp;
     const double* factor;   // Horton factor plane or nullptr
+    const double* rainp;    // FunctionalRain values per cell or nullptr
     Ctl* ctl;
     int rain_kind, infil_kind, infil_first;
     int rows;          // rows per chunk
@@ -249,7 +250,8 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
                 else f = (C)infil_t;
                 dU[0] = (S)(dU[0] - f);
             }
-            if (!do_infil && a.rain_kind != SWE_B200_RAIN_NONE) dU[0] = (S)(dU[0] + rain);
+            if (!do_infil && a.rain_kind != SWE_B200_RAIN_NONE)
+                dU[0] = (S)(dU[0] + (a.rainp ? (C)a.rainp[(size_t)j * Nx + ic] : rain));
         }
         // ================= store =================
         if (STAGE == 1) {

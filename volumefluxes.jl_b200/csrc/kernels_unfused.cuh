@@ -186,15 +186,15 @@ __global__ void k_rkavg(typename P::S* out, const typename P::S* first, long lon
 }
 // rain: out.h += r (source_term_rain.jl:73-75); infiltration: out.h -= f (source_term_infiltration.jl:85-87)
 template <class P>
-__global__ void k_point_source(typename P::S* out_h, long long n, const Ctl* c, int is_infil, const double* factor) {
+__global__ void k_point_source(typename P::S* out_h, long long n, const Ctl* c, int is_infil, const double* plane_values) {
     using S = typename P::S;
     using C = typename P::C;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
         if (is_infil) {
-            C f = factor ? (C)(factor[q] * c->infil) : (C)c->infil;
+            C f = plane_values ? (C)(plane_values[q] * c->infil) : (C)c->infil;      // Horton factor plane
             out_h[q] = (S)(out_h[q] - f);
         } else {
-            out_h[q] = (S)(out_h[q] + (C)c->rain);
+            out_h[q] = (S)(out_h[q] + (plane_values ? (C)plane_values[q] : (C)c->rain));   // FunctionalRain values
         }
     }
 }

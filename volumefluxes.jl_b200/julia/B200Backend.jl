@@ -164,6 +164,14 @@ function add_time_derivative!(sim::B200Simulator, in_buffer::Integer, out_buffer
     return ms
 end
 
+# ---- FunctionalRain (source_term_rain.jl:57-68): the closure is evaluated on the host for all cells (cell_center,
+# grid.jl:117-121) and uploaded; call before every step for a time-dependent rain_function ----------------------
+function upload_functional_rain!(sim::B200Simulator, rain::FunctionalRain, t)
+    g = sim.grid
+    vals = [Float64(rain.rain_function(t, cell_center(g, CartesianIndex(i, j))...)) for i in 1:g.totalcells[1], j in 1:g.totalcells[2]]
+    check(ccall((:swe_b200_set_rain_plane, libswe), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), sim.handle, vals, length(vals)), sim.handle)
+end
+
 # ---- scalar reductions for callbacks (examples/example_tools.jl:62-90 TotalWaterVolume collects the whole state;
 # here sum(w - B_cell) etc. are reduced on the device and 64 bytes come back) ------------------------------------
 function diagnostics(sim::B200Simulator, buffer::Integer=0)
