@@ -164,6 +164,19 @@ int swe_b200_enumerate_ghost_cells(swe_b200_handle* h, int dir, int64_t* out /*[
  * order; of THIS handle's strip in a multi-GPU run). */
 int swe_b200_diagnostics(swe_b200_handle* h, int buffer, double out[8]);
 
+/* ---- asynchronous snapshots for writer callbacks -----------------------------------------------------
+ * IntervalWriter-style callbacks (callbacks.jl:40-55; examples/example_tools.jl:113-137 writes w/hu/hv of the
+ * interior every interval) block the reference on collect(state).  snapshot_begin copies the current state to a
+ * device-side snapshot buffer on the compute stream (HBM-speed) and lets a copy stream move it to the host
+ * arrays (nx x ny per variable, like get_state_interior) while the simulation continues; snapshot_wait blocks
+ * until the host arrays are complete.  One snapshot in flight per handle (a second begin waits for the first).
+ * For the copy to overlap, the host arrays should be page-locked: swe_b200_host_alloc/free wrap
+ * cudaHostAlloc/cudaFreeHost for hosts that have no CUDA binding of their own. */
+int swe_b200_snapshot_begin(swe_b200_handle* h, void* w, void* hu, void* hv);
+int swe_b200_snapshot_wait(swe_b200_handle* h);
+void* swe_b200_host_alloc(int64_t bytes);
+int swe_b200_host_free(void* p);
+
 /* ---- multi-GPU (y-strips; one process per GPU) -------------------------------------------- */
 /* 128-byte descriptor (CUDA IPC handle + strip layout) of this rank's exchange window: the three
  * state volumes and the mailbox for halo stamps / CFL maxima.  Ranks exchange the descriptors with any

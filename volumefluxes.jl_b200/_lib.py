@@ -67,6 +67,10 @@ SYMBOLS = {
     "swe_b200_add_time_derivative": (_i, [_vp, _i, _i, _d, _pd]),
     "swe_b200_get_wavespeeds": (_i, [_vp, _vp]),
     "swe_b200_diagnostics": (_i, [_vp, C.c_int, C.POINTER(C.c_double)]),
+    "swe_b200_snapshot_begin": (_i, [_vp, _vp, _vp, _vp]),
+    "swe_b200_snapshot_wait": (_i, [_vp]),
+    "swe_b200_host_alloc": (_vp, [_i64]),
+    "swe_b200_host_free": (_i, [_vp]),
     "swe_b200_implicit_substep": (_i, [_vp, _i, _i, _d]),
     "swe_b200_post_proc_substep": (_i, [_vp, _i]),
     "swe_b200_enumerate_cells": (_i, [_vp, _vp, _pi64]),

@@ -45,7 +45,7 @@ __all__ = [
     "current_interior_state", "current_state", "current_time", "current_timestep", "perform_step",
     "simulate_to_time", "update_bc", "for_each_cell", "for_each_inner_cell", "for_each_ghost_cell",
     "cell_faces", "cell_centers", "compute_dx", "compute_dy", "inner_cells", "interior_size",
-    "simulator_from_case", "IntervalWriter", "TotalWaterVolume", "BottomTopography1D",
+    "simulator_from_case", "IntervalWriter", "TotalWaterVolume", "AsyncIntervalWriter", "Snapshot", "pinned_empty", "BottomTopography1D",
     "ShallowWaterEquations1D", "ShallowWaterEquations1DPure",
 ]
 
@@ -621,6 +621,16 @@ class Simulator:
         self._check(_lib.lib().swe_b200_get_wavespeeds(self._h, _ptr(w)))
         return w
 
+    # -- asynchronous snapshots (writer callbacks) ---------------------------------------------------
+    def snapshot_async(self, out=None):
+        """Start copying the current interior state to page-locked host arrays while the simulation goes on
+        (swe_b200_snapshot_begin); returns a Snapshot whose .wait() gives (w, hu, hv) -- (h, hu) for a 1D problem.
+        `out` may be the arrays of an earlier Snapshot (reused, no new allocation)."""
+        if out is None:
+            out = [pinned_empty((self.grid.ny, self.grid.nx), self.dtype) for _ in range(3)]
+        self._check(_lib.lib().swe_b200_snapshot_begin(self._h, *[_ptr(a) for a in out]))
+        return Snapshot(self, out, self.t)
+
     DIAG_FIELDS = ("sum_h", "sum_hu", "sum_hv", "max_h", "min_h", "wet_cells", "max_momentum", "sum_w")
 
     def diagnostics(self, buffer=0) -> dict:
@@ -731,6 +741,72 @@ class IntervalWriter:
         if t + dt >= self.current_t:
             self.writer(t, simulator)
             self.current_t += self.step
+
+
+class _PinnedBlock:
+    """a cudaHostAlloc block exposed through the array interface: numpy views keep it alive, __del__ frees it"""
+
+    def __init__(self, nbytes):
+        self.ptr = _lib.lib().swe_b200_host_alloc(int(nbytes))
+        if not self.ptr:
+            raise B200Error("cudaHostAlloc failed")
+        self.__array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(self.ptr), False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().swe_b200_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """page-locked host array (swe_b200_host_alloc): device<->host copies of it run asynchronously at PCIe speed"""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    block = _PinnedBlock(max(count * dtype.itemsize, 1))
+    return np.asarray(block)[:count * dtype.itemsize].view(dtype).reshape(shape)
+
+
+class Snapshot:
+    """state copy in flight (Simulator.snapshot_async): .wait() blocks until the host arrays are complete"""
+
+    def __init__(self, simulator, arrays, t):
+        self.simulator, self.arrays, self.t, self._done = simulator, arrays, t, False
+
+    def wait(self):
+        if not self._done:
+            self.simulator._check(_lib.lib().swe_b200_snapshot_wait(self.simulator._h))
+            self._done = True
+        if self.simulator.dim == 1:
+            return [self.arrays[0][0], self.arrays[1][0]]
+        return self.arrays
+
+
+class AsyncIntervalWriter:
+    """IntervalWriter (callbacks.jl:40-55) whose writer receives a finished host copy of the state instead of the
+    simulator: at every interval a snapshot is started and the PREVIOUS one is handed to `writer(t, (w, hu, hv))`, so
+    the device->host copy overlaps the following steps.  Call .finish() after simulate_to_time for the last one."""
+
+    def __init__(self, step: float, writer: Callable):
+        self.step, self.writer, self.current_t, self._pending, self._spare = float(step), writer, 0.0, None, None
+
+    def _flush(self):
+        if self._pending is not None:
+            snap = self._pending
+            self.writer(snap.t, snap.wait())
+            self._spare, self._pending = snap.arrays, None
+
+    def __call__(self, t, simulator):
+        if t + simulator.dt >= self.current_t:
+            self._flush()
+            self._pending = simulator.snapshot_async(self._spare)
+            self._spare = None
+            self.current_t += self.step
+
+    def finish(self):
+        self._flush()
 
 
 class TotalWaterVolume:

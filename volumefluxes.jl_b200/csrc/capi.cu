@@ -85,6 +85,14 @@ int swe_b200_get_faces(swe_b200_handle* h, void* l, void* r) { FWD(get_faces(l, 
 int swe_b200_add_time_derivative(swe_b200_handle* h, int ib, int ob, double t, double ms[2]) { FWD(add_time_derivative(ib, ob, t, ms)); }
 int swe_b200_get_wavespeeds(swe_b200_handle* h, void* w) { FWD(get_wavespeeds(w)); }
 int swe_b200_diagnostics(swe_b200_handle* h, int b, double out[8]) { FWD(diagnostics(b, out)); }
+int swe_b200_snapshot_begin(swe_b200_handle* h, void* w, void* hu, void* hv) { FWD(snapshot_begin(w, hu, hv)); }
+int swe_b200_snapshot_wait(swe_b200_handle* h) { FWD(snapshot_wait()); }
+void* swe_b200_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+int swe_b200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? SWE_B200_OK : SWE_B200_ECUDA; }
 int swe_b200_implicit_substep(swe_b200_handle* h, int ob, int pb, double dt) { FWD(implicit_substep(ob, pb, dt)); }
 int swe_b200_post_proc_substep(swe_b200_handle* h, int b) { FWD(post_proc_substep(b)); }
 int swe_b200_enumerate_cells(swe_b200_handle* h, int64_t* out, int64_t* n) { FWD(enumerate(0, 0, 0, out, n)); }

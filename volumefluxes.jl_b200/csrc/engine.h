@@ -31,6 +31,8 @@ struct Engine {
     virtual int add_time_derivative(int in_buffer, int out_buffer, double t, double maxspeed[2]) = 0;
     virtual int get_wavespeeds(void* ws) = 0;
     virtual int diagnostics(int buffer, double out[8]) = 0;
+    virtual int snapshot_begin(void* w, void* hu, void* hv) = 0;
+    virtual int snapshot_wait() = 0;
     virtual int implicit_substep(int out_buffer, int prev_buffer, double dt) = 0;
     virtual int post_proc_substep(int buffer) = 0;
     virtual int enumerate(int kind, int dir, int ghostcells, int64_t* out, int64_t* count) = 0;

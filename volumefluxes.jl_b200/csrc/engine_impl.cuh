@@ -176,6 +176,10 @@ public:
         cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(rainp); cudaFree(ctl); cudaFree(d_items[0]); cudaFree(d_items[1]); cudaFree(diag_buf);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (auto e : ev) cudaEventDestroy(e);
+        cudaFree(snap);
+        if (snap_ready) cudaEventDestroy(snap_ready);
+        if (snap_done) cudaEventDestroy(snap_done);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -469,6 +473,37 @@ public:
         if (rc) return rc;
         SWE_CUDA(cudaMemcpyAsync(w, ws, sizeof(S) * plane, cudaMemcpyDeviceToHost, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
+        return SWE_B200_OK;
+    }
+    // asynchronous snapshot: state -> device snapshot buffer on the compute stream (so the following steps may
+    // overwrite the volumes), then device -> host on a copy stream while the simulation continues
+    S* snap = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
+    bool snap_pending = false;
+    int snapshot_begin(void* w, void* hu, void* hv) override {
+        if (!snap) {
+            SWE_CUDA(cudaMalloc(&snap, sizeof(S) * plane * 3));
+            SWE_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            SWE_CUDA(cudaEventCreateWithFlags(&snap_ready, cudaEventDisableTiming));
+            SWE_CUDA(cudaEventCreateWithFlags(&snap_done, cudaEventDisableTiming));
+        }
+        if (snap_pending) SWE_CUDA(cudaStreamWaitEvent(stream, snap_done, 0));     // the previous snapshot still reads `snap`
+        SWE_CUDA(cudaMemcpyAsync(snap, vol[cur[0]], sizeof(S) * plane * 3, cudaMemcpyDeviceToDevice, stream));
+        SWE_CUDA(cudaEventRecord(snap_ready, stream));
+        SWE_CUDA(cudaStreamWaitEvent(copy_stream, snap_ready, 0));
+        void* dst[3] = {w, hu, hv};
+        for (int k = 0; k < 3; ++k)
+            SWE_CUDA(cudaMemcpy2DAsync(dst[k], sizeof(S) * cfg.nx, snap + (size_t)k * plane + (size_t)gc * Nx + gc, sizeof(S) * Nx,
+                                       sizeof(S) * cfg.nx, cfg.ny, cudaMemcpyDeviceToHost, copy_stream));
+        SWE_CUDA(cudaEventRecord(snap_done, copy_stream));
+        snap_pending = true;
+        return SWE_B200_OK;
+    }
+    int snapshot_wait() override {
+        if (!snap_pending) return SWE_B200_OK;
+        SWE_CUDA(cudaEventSynchronize(snap_done));
+        snap_pending = false;
         return SWE_B200_OK;
     }
     // scalar reductions over the interior of a buffer (TotalWaterVolume-style callbacks): 64 bytes come back

@@ -172,6 +172,19 @@ function upload_functional_rain!(sim::B200Simulator, rain::FunctionalRain, t)
     check(ccall((:swe_b200_set_rain_plane, libswe), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), sim.handle, vals, length(vals)), sim.handle)
 end
 
+# ---- asynchronous snapshots for writer callbacks (callbacks.jl:40-55, examples/example_tools.jl:113-137): the copy to
+# the (page-locked) host arrays overlaps the following steps; wait_snapshot! before reading them ------------------
+function pinned_array(::Type{T}, dims...) where {T}
+    p = ccall((:swe_b200_host_alloc, libswe), Ptr{Cvoid}, (Int64,), sizeof(T) * prod(dims))
+    p == C_NULL && error("cudaHostAlloc failed")
+    a = unsafe_wrap(Array, Ptr{T}(p), dims; own=false)
+    finalizer(_ -> ccall((:swe_b200_host_free, libswe), Cint, (Ptr{Cvoid},), p), a)
+    return a
+end
+begin_snapshot!(sim::B200Simulator{T}, w::Array{T}, hu::Array{T}, hv::Array{T}) where {T} =
+    check(ccall((:swe_b200_snapshot_begin, libswe), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ptr{T}), sim.handle, w, hu, hv), sim.handle)
+wait_snapshot!(sim::B200Simulator) = check(ccall((:swe_b200_snapshot_wait, libswe), Cint, (Ptr{Cvoid},), sim.handle), sim.handle)
+
 # ---- scalar reductions for callbacks (examples/example_tools.jl:62-90 TotalWaterVolume collects the whole state;
 # here sum(w - B_cell) etc. are reduced on the device and 64 bytes come back) ------------------------------------
 function diagnostics(sim::B200Simulator, buffer::Integer=0)
