@@ -134,13 +134,38 @@ class ClockSampler:
                 "source": "nvidia-smi -lms 100"}
 
 
-def build_case(n: int, dtype: str, ny=None):
+# BASELINE.json configs[1..4] (SURVEY 8d "Config 2..5"): (builder, default n, dtype, algorithmic words per cell of
+# K1 / K2 in the state's element size, description).  Config 5 is the bench line; 2-4 are side measurements.
+CONFIGS = {
+    2: ("swashes", 1024, "float64", 6, 9,
+        "configs[1]: 2D SWASHES 4.1.2 dam break on a dry bed, WallBC, flat bottom (no bathymetry words), "
+        "LinearReconstruction(1.2), RungeKutta2, cfl 0.1, depth_cutoff = kappa = 1e-7"),
+    3: ("terrain", 4096, "float32", 9, 12,
+        "configs[2]: terrain.jl-shaped synthetic terrain, lake at level 1, bottom source, ConstantRain, Horton infiltration "
+        "(Float64 factor plane = 2 words), ImplicitFriction(bsa2012), LinearReconstruction(1.2), RungeKutta2, cfl 0.25"),
+    4: ("urban", 8192, "float32", 7, 10,
+        "configs[3]: urban.jl-style synthetic DEM with buildings, lake at level 1, NoReconstruction, rain + constant "
+        "infiltration, bottom source, ImplicitFriction(bsa2012), RungeKutta2, cfl 0.1, depth_cutoff = kappa = 8e-2"),
+    5: ("lake", 16384, "float32", 7, 10, None),
+}
+
+
+def build_case(n: int, dtype: str, ny=None, config: int = 5):
     import cases
+    kind = CONFIGS[config][0]
+    if kind == "swashes":
+        return cases.swashes_dambreak_2d(n=n, dtype=dtype)
+    if kind == "terrain":
+        return cases.terrain_case(n=n, dtype=dtype, level=1.0)
+    if kind == "urban":
+        return cases.urban_case(n=n, dtype=dtype, level=1.0)
     return cases.lake_case(n=n, ny=ny, dtype=dtype, level=0.0)
 
 
 def wet_fraction(case, state):
     import cases
+    if not isinstance(case.get("B"), np.ndarray):
+        return float(np.mean(state[0].astype(np.float64) >= case["depth_cutoff"]))
     Bc = cases.synthetic().cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
     return float(np.mean(state[0].astype(np.float64) - Bc >= case["depth_cutoff"]))
 
@@ -160,7 +185,7 @@ def run_reference(args, rank):
     from oracle import oracle
     threads = oracle.set_threads(os.cpu_count() or 1)
     n = args.cpu_n
-    case, state = build_case(n, args.dtype)
+    case, state = build_case(n, args.dtype, config=args.config)
     o = oracle.OracleSim(case)
     o.set_state_interior(*state)
     for _ in range(args.warmup):
@@ -186,6 +211,11 @@ def run_reference(args, rank):
 
 
 def workload_config(args, n, wet):
+    if args.config != 5:
+        return {"workload": f"{CONFIGS[args.config][5]}; {n}x{n} {args.dtype}, {wet:.0%} of cells wet",
+                "grid": [n, n], "arithmetic": "fast" if not args.strict else "strict", "parallelism": "single GPU",
+                "l2": "3 volumes of %.0f MB" % (3 * 3 * (n + 4) ** 2 * np.dtype(args.dtype).itemsize / 1e6)
+                      + (" fit the 126 MB L2: an L2 flush (256 MB memset) runs between timed steps" if args.flush_l2 else "")}
     return {"workload": f"configs[4]: {n}x{n} {args.dtype} synthetic bathymetry (separable 5-octave hills, seed 1234), "
                         f"lake at level 0 + Gaussian hump ({wet:.0%} of cells wet), WallBC, LinearReconstruction(1.2), "
                         "CentralUpwind, SourceTermBottom, ImplicitFriction(bh2021), RungeKutta2, cfl 0.25, "
@@ -228,7 +258,7 @@ def run_ours(args, rank, world):
                 case, state, y0 = cases.lake_strip_case(n, rank, world, dtype=args.dtype, rows=(offs[rank], sizes[rank]))
                 rows = case["ny"]
     else:
-        case, state = build_case(n, args.dtype, ny=args.ny)
+        case, state = build_case(n, args.dtype, ny=args.ny, config=args.config)
         y0, rows = 0, (args.ny or n)
     wet = wet_fraction(case, state)
     # pinned host buffers for the end-to-end leg
@@ -268,11 +298,22 @@ def run_ours(args, rank, world):
         return float(t.item())
 
     # ---- device-resident leg: inputs already in HBM when the timed region starts -------------------
-    sim.run_steps(args.warmup)
+    sim.run_steps(args.warmup, case.get("maximum_timestep"))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    tm = sim.run_steps_timed(args.steps)       # CUDA events on the library's stream around the K steps
+    mts = case.get("maximum_timestep")
+    if args.flush_l2 and world == 1:
+        # the working set fits the 126 MB L2: write a 256 MB buffer between timed steps, time every step on its own
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        tm = None
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            one = sim.run_steps_timed(1, mts)
+            tm = one if tm is None else {k: tm[k] + one[k] for k in tm}
+    else:
+        tm = sim.run_steps_timed(args.steps, mts)       # CUDA events on the library's stream around the K steps
     barrier()
     clocks = sampler.stop()
     cells = n * (args.ny or n) if world == 1 else n * n
@@ -288,7 +329,7 @@ def run_ours(args, rank, world):
     barrier()
     t0 = time.perf_counter()
     sim._check(L.swe_b200_set_state_interior(sim._h, *[ptr(p) for p in pinned]))
-    sim.run_steps(args.steps)
+    sim.run_steps(args.steps, case.get("maximum_timestep"))
     sim._check(L.swe_b200_get_state_interior(sim._h, *[ptr(p) for p in out_pinned]))
     e2e_sec = max_over_ranks(time.perf_counter() - t0)
     itemsize = np.dtype(args.dtype).itemsize
@@ -312,10 +353,11 @@ def run_ours(args, rank, world):
         return
 
     peak, peak_src = hbm_peak()
+    W1, W2 = CONFIGS[args.config][3], CONFIGS[args.config][4]
     ns2 = max(tm["stage_launches"] // 2, 1)
     k2_ms = tm["stage2_ms"] / ns2
     k1_ms = tm["stage1_ms"] / ns2
-    achieved = WORDS_STAGE2 * itemsize * cells_local / (k2_ms * 1e-3) / 1e9
+    achieved = W2 * itemsize * cells_local / (k2_ms * 1e-3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
@@ -323,13 +365,13 @@ def run_ours(args, rank, world):
             traffic = json.loads(tf.read_text()).get(f"k_stage2_{args.dtype}_{n}")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "x2::k_stage_x2<RECON=1, HASB=1, STAGE=2, FRIC=1> (K2: RK2 stage 2, fused)" if args.dtype == "float32" and not args.strict else "k_stage<..., STAGE=2> (K2)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": ("x2::k_stage_x2<RECON=1, HASB=1, STAGE=2, FRIC=1> (K2: RK2 stage 2, fused)" if args.config == 5 else "x2::k_stage_x2<..., STAGE=2> (K2: RK2 stage 2, fused)") if args.dtype == "float32" and not args.strict and not args.unfused else "k_stage<..., STAGE=2> (K2, generic fused kernel)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": WORDS_STAGE2 * itemsize * cells_local,
+                "algorithmic_bytes_per_launch": W2 * itemsize * cells_local,
                 "avg_launch_ms": k2_ms, "per": "GPU (rank 0's strip)" if world > 1 else "GPU",
-                "k1": {"achieved": WORDS_STAGE1 * itemsize * cells_local / (k1_ms * 1e-3) / 1e9, "avg_launch_ms": k1_ms},
-                "step": {"achieved": (WORDS_STAGE1 + WORDS_STAGE2) * itemsize * cells_local * args.steps / sec / 1e9,
-                         "frac": (WORDS_STAGE1 + WORDS_STAGE2) * itemsize * cells_local * args.steps / sec / 1e9 / peak}}
+                "k1": {"achieved": W1 * itemsize * cells_local / (k1_ms * 1e-3) / 1e9, "avg_launch_ms": k1_ms},
+                "step": {"achieved": (W1 + W2) * itemsize * cells_local * args.steps / sec / 1e9,
+                         "frac": (W1 + W2) * itemsize * cells_local * args.steps / sec / 1e9 / peak}}
 
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----------------
     cpu = None
@@ -337,7 +379,7 @@ def run_ours(args, rank, world):
         from oracle import oracle
         oracle.set_threads(1)
         cn = args.cpu_n
-        ccase, cstate = build_case(cn, args.dtype)
+        ccase, cstate = build_case(cn, args.dtype, config=args.config)
         o = oracle.OracleSim(ccase)
         o.set_state_interior(*cstate)
         o.step()
@@ -378,8 +420,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=16384)
-    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
+                    help="BASELINE config (SURVEY 8d numbering): 5 = the bench line (16384^2 Float32); 2-4 = side measurements, N = 1")
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--dtype", default=None, choices=["float32", "float64"])
     ap.add_argument("--cpu-n", type=int, default=1024, dest="cpu_n")
     ap.add_argument("--cpu-steps", type=int, default=30, dest="cpu_steps", help="RK2 steps of the cpu_baseline sample")
     ap.add_argument("--strict", action="store_true")
@@ -391,6 +435,9 @@ def main():
     ap.add_argument("--dry-cost", type=float, default=0.6, dest="dry_cost",
                     help="cost of a dry cell relative to a wet one in the strip balancing model")
     args = ap.parse_args()
+    args.n = args.n or CONFIGS[args.config][1]
+    args.dtype = args.dtype or CONFIGS[args.config][2]
+    args.flush_l2 = 3 * 3 * (args.n + 4) * ((args.ny or args.n) + 4) * np.dtype(args.dtype).itemsize < 4 * 126e6
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -224,7 +224,9 @@ public:
         const int ntiles = (c.nx + x2::VW - 1) / x2::VW;
         const long long W = 148LL * (stage == 2 ? x2::minb<2>() : x2::minb<1>()) * x2::WPB;
         const long long L = (long long)ntiles * c.ny;
-        int sizes[4] = {big, 63, 30, 12};
+        // small grids: a big item is at most about half of a warp's whole share of tile-rows
+        if (!std::getenv("SWE_B200_X2_ROWS")) big = (int)std::min<long long>(big, std::max<long long>(12, L / W / 2 / 3 * 3));
+        int sizes[4] = {big, std::min(63, std::max(12, big / 2 / 3 * 3)), std::min(30, std::max(12, big / 4 / 3 * 3)), 12};
         long long quota[4];
         double per_warp[4] = {0, 1, 1, 1};          // least items of each small class per resident warp
         if (const char* e = std::getenv("SWE_B200_X2_Q")) sscanf(e, "%lf,%lf,%lf", &per_warp[1], &per_warp[2], &per_warp[3]);
@@ -622,8 +624,14 @@ public:
         StageArgs<P> a;
         a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.Bp = Bp; a.factor = factor; a.rainp = rainp; a.ctl = ctl;
         a.rain_kind = cfg.rain_kind; a.infil_kind = cfg.infil_kind; a.infil_first = cfg.infil_first;
-        a.rows = FUSED_ROWS;
+        // rows marched per block: 64 on large grids (the 4-row prologue amortises); halved until the launch has at
+        // least two waves of 16 warps per SM (a 1024^2 grid at 64 rows is 640 warps: one per scheduler, latency-bound;
+        // measured 1024^2 Float64: 64 rows 0.340, 32: 0.213, 16: 0.174, 8: 0.160 ms/step)
         const int nwarps = (cfg.nx + FUSED_VW - 1) / FUSED_VW;
+        a.rows = FUSED_ROWS;
+        if (const char* e = std::getenv("SWE_B200_FUSED_ROWS")) a.rows = std::max(4, atoi(e));
+        else
+            while (a.rows > 8 && (long long)nwarps * ((cfg.ny + a.rows - 1) / a.rows) < 148LL * 32) a.rows /= 2;
         dim3 g((nwarps + FUSED_WPB - 1) / FUSED_WPB, (cfg.ny + a.rows - 1) / a.rows);
         dim3 b(FUSED_WPB * 32);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
