@@ -624,14 +624,22 @@ public:
         StageArgs<P> a;
         a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.Bp = Bp; a.factor = factor; a.rainp = rainp; a.ctl = ctl;
         a.rain_kind = cfg.rain_kind; a.infil_kind = cfg.infil_kind; a.infil_first = cfg.infil_first;
-        // rows marched per block: 64 on large grids (the 4-row prologue amortises); halved until the launch has at
-        // least two waves of 16 warps per SM (a 1024^2 grid at 64 rows is 640 warps: one per scheduler, latency-bound;
-        // measured 1024^2 Float64: 64 rows 0.340, 32: 0.213, 16: 0.174, 8: 0.160 ms/step)
+        // rows marched per block: every block pays a ~4.5-row prologue, and the launch runs in waves of 148 x 4
+        // resident blocks, so the rows are chosen to minimise waves x (rows + 4.5).  Large grids end up near 64; a
+        // 1024^2 grid gets 18 rows = one full wave (at 64 rows it would be 640 warps, one per scheduler:
+        // measured 1024^2 Float64 K1+K2 per step: 64 rows 0.318, 32: 0.191, 16: 0.153, 8: 0.138 ms).
         const int nwarps = (cfg.nx + FUSED_VW - 1) / FUSED_VW;
+        const long long nbx = (nwarps + FUSED_WPB - 1) / FUSED_WPB;
         a.rows = FUSED_ROWS;
         if (const char* e = std::getenv("SWE_B200_FUSED_ROWS")) a.rows = std::max(4, atoi(e));
-        else
-            while (a.rows > 8 && (long long)nwarps * ((cfg.ny + a.rows - 1) / a.rows) < 148LL * 32) a.rows /= 2;
+        else {
+            double best = 1e300;
+            for (int r = 6; r <= FUSED_ROWS; ++r) {
+                const long long blocks = nbx * ((cfg.ny + r - 1) / r);
+                const double cost = (double)((blocks + 148 * 4 - 1) / (148 * 4)) * (r + 4.5);
+                if (cost <= best) { best = cost; a.rows = r; }
+            }
+        }
         dim3 g((nwarps + FUSED_WPB - 1) / FUSED_WPB, (cfg.ny + a.rows - 1) / a.rows);
         dim3 b(FUSED_WPB * 32);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
