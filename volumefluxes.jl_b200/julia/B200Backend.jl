@@ -78,7 +78,7 @@ function Simulator(backend::B200Backend{T}, system, timestepper, grid::Cartesian
         eq isa AllPureSWE ? 1 : 0, system.reconstruction isa LinearReconstruction ? 1 : 0,
         timestepper isa RungeKutta2 ? 1 : 0, friction_code(fr), hasB ? 1 : 0,
         any(s -> s isa SourceTermBottom, system.source_terms) ? 1 : 0,
-        rain isa ConstantRain ? 1 : rain isa TimeDependentRain ? 2 : 0,
+        rain isa ConstantRain ? 1 : rain isa TimeDependentRain ? 2 : rain isa FunctionalRain ? 3 : 0,
         inf isa ConstantInfiltration ? 1 : inf isa HortonInfiltration ? 2 : 0, infil_first ? 1 : 0,
         rain isa TimeDependentRain ? length(rain.rain_rates) : 0, backend.strict ? 1 : 0, backend.fused ? 1 : 0,
         backend.device, 0, 1, interior_size(grid)[2], 0, (Int32(0), Int32(0), Int32(0)),
@@ -103,8 +103,11 @@ function Simulator(backend::B200Backend{T}, system, timestepper, grid::Cartesian
         f = Array{Float64}(inf.factor)
         check(ccall((:swe_b200_set_infiltration_factor, libswe), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), sim.handle, f, length(f)), sim.handle)
     end
+    rain isa FunctionalRain && upload_functional_rain!(sim, rain, t0)     # values of the closure at t0 (see below)
     return sim
 end
+
+functional_rain(sim::B200Simulator) = (r = filter(s -> s isa FunctionalRain, sim.system.source_terms); isempty(r) ? nothing : r[1])
 
 # simulator.jl:119-139 -- new_state is an (nx, ny) array of SVector{3} (or three scalar arrays)
 function set_current_state!(sim::B200Simulator{T}, new_state) where {T}
@@ -129,12 +132,17 @@ current_time(sim::B200Simulator) = time_and_step(sim)[1]
 current_timestep(sim::B200Simulator) = time_and_step(sim)[2]
 
 # simulator.jl:145-177
-perform_step!(sim::B200Simulator, max_dt) =
+function perform_step!(sim::B200Simulator, max_dt)
+    fr = functional_rain(sim)       # a (possibly time-dependent) closure: re-evaluate it at the time of this step
+    isnothing(fr) || upload_functional_rain!(sim, fr, current_time(sim))
     check(ccall((:swe_b200_step, libswe), Cint, (Ptr{Cvoid}, Float64, Cint), sim.handle, max_dt, 0), sim.handle)
+end
 
 # simulator.jl:179-212.  Without callback: device-resident loop; with callback: the reference's host loop.
 function simulate_to_time(sim::B200Simulator, endtime; match_endtime=true, callback=nothing,
                           show_progress=true, maximum_timestep=nothing)
+    fr = functional_rain(sim)
+    isnothing(fr) || isnothing(callback) && (callback = (t, s) -> nothing)   # the closure needs the host between steps
     if isnothing(callback)
         n = Ref{Int64}(0)
         check(ccall((:swe_b200_simulate_to_time, libswe), Cint, (Ptr{Cvoid}, Float64, Cint, Float64, Ref{Int64}),
@@ -146,6 +154,7 @@ function simulate_to_time(sim::B200Simulator, endtime; match_endtime=true, callb
     while t < endtime
         max_dt = match_endtime ? endtime - t : Inf
         isnothing(maximum_timestep) || (max_dt = min(max_dt, maximum_timestep))
+        isnothing(fr) || upload_functional_rain!(sim, fr, t)
         check(ccall((:swe_b200_step, libswe), Cint, (Ptr{Cvoid}, Float64, Cint), sim.handle, max_dt, 1), sim.handle)
         t = current_time(sim)
         callback(t, sim)
