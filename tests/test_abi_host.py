@@ -145,3 +145,30 @@ def test_x2_kernels_sass_has_packed_fp32_and_async_copies():
         assert m, f"no ptxas record for {k}"
         assert (int(m.group(2)), int(m.group(3))) == (0, 0), f"{k} spills: {m.group(0)}"
         assert int(m.group(4)) <= regs
+
+
+def test_partition_rows_properties(pkg):
+    """property test (hypothesis) of the strip partition: exact cover, >= 4 rows each, and with a cost the heaviest
+    strip is within one row's cost (plus the 4-row floor) of the ideal share"""
+    from hypothesis import given, settings, strategies as st
+    mg = pkg.multigpu
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 8), st.integers(0, 400), st.integers(0, 2 ** 31 - 1), st.booleans())
+    def check(nranks, extra, seed, with_cost):
+        ny = 4 * nranks + extra
+        cost = None
+        if with_cost:
+            rng = np.random.default_rng(seed)
+            cost = mg.row_cost_from_wet_fraction(rng.random(ny) ** rng.integers(1, 4), dry_cost=float(rng.uniform(0.2, 1.0)))
+        offs, sizes = mg.partition_rows(ny, nranks, cost)
+        assert len(offs) == len(sizes) == nranks and sum(sizes) == ny and offs[0] == 0
+        assert all(s >= 4 for s in sizes)
+        assert all(offs[r + 1] == offs[r] + sizes[r] for r in range(nranks - 1))
+        if cost is None:
+            assert max(sizes) - min(sizes) <= 1
+        elif ny >= 16 * nranks:
+            loads = [float(cost[o:o + s].sum()) for o, s in zip(offs, sizes)]
+            assert max(loads) <= cost.sum() / nranks + 2 * cost.max() + 1e-9
+
+    check()
