@@ -207,9 +207,8 @@ public:
         q.botx = s2(c.has_bottom_source ? -0.25 * c.g / dx : 0.0); q.boty = s2(c.has_bottom_source ? -0.25 * c.g / dy : 0.0); q.Cz = s2(c.Cz);
         q.rows = 126;
         if (const char* e = std::getenv("SWE_B200_X2_ROWS")) q.rows = std::max(3, atoi(e) / 3 * 3);   // multiple of 3
-        build_items(c, q.rows, 1);
-        build_items(c, q.rows, 2);
-        x2_ok = true;
+        // (if the item tables cannot be allocated the generic fused kernels serve the configuration)
+        x2_ok = build_items(c, q.rows, 1) && build_items(c, q.rows, 2);
     }
     // Guided schedule of the persistent warps: every tile column (60 output columns) is cut into row segments;
     // most rows go into `big`-row items (the 4-row prologue amortises), the rest into three classes of ever
@@ -220,7 +219,7 @@ public:
     // 1/2, 1/4, 1/4 over the small classes; measured 1-4 % slower on 2048..16384-row grids: more small items.)
     int4* d_items[2] = {nullptr, nullptr};
     int n_items[2] = {0, 0};
-    void build_items(const swe_b200_config& c, int big, int stage) {
+    bool build_items(const swe_b200_config& c, int big, int stage) {
         const int ntiles = (c.nx + x2::VW - 1) / x2::VW;
         const long long W = 148LL * (stage == 2 ? x2::minb<2>() : x2::minb<1>()) * x2::WPB;
         const long long L = (long long)ntiles * c.ny;
@@ -272,8 +271,13 @@ public:
         const int s = stage - 1;
         n_items[s] = (int)items.size();
         if (d_items[s]) cudaFree(d_items[s]);
-        cudaMalloc(&d_items[s], sizeof(int4) * items.size());
-        cudaMemcpy(d_items[s], items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice);
+        d_items[s] = nullptr;
+        if (cudaMalloc(&d_items[s], sizeof(int4) * items.size()) != cudaSuccess ||
+            cudaMemcpy(d_items[s], items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return true;
     }
 
     template <int STAGE>
