@@ -27,6 +27,11 @@ namespace swe {
 constexpr int FUSED_VW = 28;     // valid (output) columns per warp
 constexpr int FUSED_WPB = 4;     // warps per block
 constexpr int FUSED_ROWS = 64;   // rows marched per block
+// unroll of the row march: the register windows (state rows, U^n rows, corner rows) rotate with period 3
+#ifndef FUSED_UNROLL
+#define FUSED_UNROLL 2
+#endif
+constexpr int FUSED_UNROLL_N = FUSED_UNROLL;
 
 template <class P>
 struct StageArgs {
@@ -61,8 +66,14 @@ __device__ __forceinline__ void substep_tail(const Par<typename P::C>& p, const 
     for (int k = 0; k < 3; ++k) o[k] = (S)(st[k] + dt * d[k]);
     if (p.friction != SWE_B200_FRICTION_NONE) {
         const C den = friction_denominator<P, false>(p, st[0], st[1], st[2], Bm, dt_s);
-        o[1] = (S)(o[1] / den);
-        o[2] = (S)(o[2] / den);
+        if constexpr (P::strict) {
+            o[1] = (S)(o[1] / den);
+            o[2] = (S)(o[2] / den);
+        } else {
+            const C rden = rcp_fast(den);
+            o[1] = (S)(o[1] * rden);
+            o[2] = (S)(o[2] * rden);
+        }
     }
     post_proc_cell<P>(p, o, Bm);
 }
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
     S ru[3], rd[3] = {0, 0, 0}, pa = 0, pb = 0;          // prefetched raw row j+2 and corner row j+3
     issue_row(min(ja + 2, Ny - 1), ru, rd);
     load_corners(min(ja + 3, Ny), pa, pb);
-#pragma unroll 2
+#pragma unroll FUSED_UNROLL_N
     for (int j = ja; j < jb; ++j) {
         // window: qm = row j-1, q0 = row j, q1 = row j+1 ; corners ca[0..2] = rows j..j+2
         ca[3] = pa;                                        // corner row j+3: bcell(j+2) (stage 2 / RECON 0)
@@ -272,8 +283,14 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
             const C Bm = bcell_of(0);
             if (p.friction != SWE_B200_FRICTION_NONE) {
                 const C den = friction_denominator<P, false>(p, q0[0], q0[1], q0[2], Bm, dt_s);
-                o[1] = (S)(o[1] / den);
-                o[2] = (S)(o[2] / den);
+                if constexpr (P::strict) {
+                    o[1] = (S)(o[1] / den);
+                    o[2] = (S)(o[2] / den);
+                } else {
+                    const C rden = rcp_fast(den);
+                    o[1] = (S)(o[1] * rden);
+                    o[2] = (S)(o[2] * rden);
+                }
             }
             post_proc_cell<P>(p, o, Bm);
             if (out_lane) {

@@ -41,9 +41,34 @@ struct Par {
 
 // ---- small math helpers (overloads keep the float versions in float) ----------------------
 __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+// Float64 has no native min/max instruction on sm_100a: fmin/fmax (IEEE NaN and signed-zero semantics) cost ~9
+// instructions each, a compare-and-select 3.  The fast translation unit (SWE_FAST_MINMAX, engine_fast.cu) uses the
+// latter -- identical values for finite, non-zero-tie arguments; the strict one keeps fmin/fmax (Julia's min/max).
+#ifdef SWE_FAST_MINMAX
+__device__ __forceinline__ double mn(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double mx(double a, double b) { return a > b ? a : b; }
+#else
 __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
-__device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+#endif
+__device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+// reciprocal for the fast policies.  Float32: a plain division (-use_fast_math makes it MUFU.RCP).  Float64: the IEEE
+// division is ~20 instructions plus a slow-path call; SWE_FAST_DIV64 (engine_fast.cu) replaces it by the hardware
+// seed (rcp.approx.ftz.f64, ~2^-20) and two Newton steps (4 DFMA): relative error ~1 ulp for normal arguments --
+// every argument on this path is a desingularised depth, a wave-speed gap >= kappa or a friction denominator >= 1.
+__device__ __forceinline__ float rcp_fast(float x) { return 1.0f / x; }
+__device__ __forceinline__ double rcp_fast(double x) {
+#ifdef SWE_FAST_DIV64
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
 __device__ __forceinline__ float ab(float a) { return fabsf(a); }
 __device__ __forceinline__ double ab(double a) { return fabs(a); }
 __device__ __forceinline__ float sq(float a) { return sqrtf(a); }
@@ -124,7 +149,7 @@ __device__ __forceinline__ void flux_eig(const Par<typename P::C>& p, typename P
             u = hu / hstar;
             v = hv / hstar;
         } else {
-            C r = (C)1 / hstar;
+            C r = rcp_fast(hstar);
             u = hu * r;
             v = hv * r;
         }
@@ -192,7 +217,7 @@ __device__ __forceinline__ void central_upwind(const Par<typename P::C>& p, cons
             F[k] = ok ? val : (C)0;
         }
     } else {
-        const C r = ok ? (C)1 / d : (C)0;
+        const C r = ok ? rcp_fast(d) : (C)0;
         const C c2 = ap * am * r;
 #pragma unroll
         for (int k = 0; k < 3; ++k) F[k] = (ap * Fm[k] - am * Fp[k]) * r + c2 * (C)(fp[k] - fm[k]);
@@ -279,15 +304,21 @@ __device__ __forceinline__ typename P::C friction_denominator(const Par<typename
     C hstar;
     if constexpr (PURE) hstar = pw - (C)0.0;
     else hstar = desing_practical<P, C>(p, pw - Bm);
-    C u = phu / hstar;
-    C v = phv / hstar;
-    C speed = sq(u * u + v * v);
     C denom;
     if (p.friction == SWE_B200_FRICTION_BH2021) denom = hstar * hstar;
     else if (p.friction == SWE_B200_FRICTION_BSA2012) denom = cb(hstar) * hstar;
     else denom = cb(hstar) * hstar * hstar;
-    C fs = -p.Cz * speed / denom;
-    return (C)1 - dt_s * fs;
+    if constexpr (P::strict) {
+        C u = phu / hstar;
+        C v = phv / hstar;
+        C speed = sq(u * u + v * v);
+        C fs = -p.Cz * speed / denom;
+        return (C)1 - dt_s * fs;
+    } else {      // |(hu, hv)| / (|h*| denom) with one reciprocal
+        C speed = sq((C)phu * phu + (C)phv * phv);
+        C fs = p.Cz * speed * rcp_fast(ab(hstar) * denom);
+        return (C)1 + dt_s * fs;
+    }
 }
 
 // ---- dry-cell clean-up, timestepper.jl:41-51 ---------------------------------------------------------
