@@ -172,3 +172,41 @@ def test_partition_rows_properties(pkg):
             assert max(loads) <= cost.sum() / nranks + 2 * cost.max() + 1e-9
 
     check()
+
+
+def test_grid_helpers_match_reference_tests(pkg):
+    """test_grid.jl:24-48 and test_grid_2d.jl:25-74 on the host mirror (CartesianGrid 1D / 2D, cell_faces,
+    cell_centers incl. the ghost region, compute_dx / compute_dy)."""
+    P = pkg
+    nx, ny, gc = 10, 6, 2
+    g1 = P.CartesianGrid(nx, gc=2, extent=[0, nx])
+    assert g1.dim == 1 and g1.totalcells == (nx + 4,) and P.compute_dx(g1) == 1.0
+    g = P.CartesianGrid(nx, ny, gc=gc, extent=[[0, nx], [0, ny]])
+    assert P.compute_dx(g) == 1.0 and P.compute_dy(g) == 1.0 and P.interior_size(g) == (nx, ny)
+    xf, yf = np.arange(nx + 1.0), np.arange(ny + 1.0)
+    xc, yc = np.arange(0.5, nx), np.arange(0.5, ny)
+    assert np.array_equal(P.cell_faces(g, P.XDIR), xf) and np.array_equal(P.cell_faces(g, P.YDIR), yf)
+    assert np.array_equal(P.cell_centers(g, P.XDIR), xc) and np.array_equal(P.cell_centers(g, P.YDIR), yc)
+    f2, c2 = P.cell_faces(g), P.cell_centers(g)              # [j, i, (x, y)] == the reference's [i, j][1:2]
+    assert f2.shape == (ny + 1, nx + 1, 2) and c2.shape == (ny, nx, 2)
+    assert np.array_equal(f2[..., 0], np.tile(xf, (ny + 1, 1))) and np.array_equal(f2[..., 1], np.tile(yf[:, None], (1, nx + 1)))
+    assert np.array_equal(c2[..., 0], np.tile(xc, (ny, 1))) and np.array_equal(c2[..., 1], np.tile(yc[:, None], (1, nx)))
+    fg = P.cell_faces(g, interior=False)
+    assert np.allclose(fg[2:-2, 2:-2], f2, atol=1e-14)
+    cg = P.cell_centers(g, interior=False)
+    assert np.allclose(cg[2:-2, 2:-2], c2, atol=1e-14)
+    for j in (1, 2):
+        for i in (1, 2):
+            assert np.allclose(fg[j - 1, i - 1], [-3 + i, -3 + j], atol=1e-14)
+            assert np.allclose(fg[-j, -i], [nx + (gc - i + 1), ny + (gc - j + 1)], atol=1e-14)
+            assert np.allclose(cg[j - 1, i - 1], [-3 + i + 0.5, -3 + j + 0.5], atol=1e-14)
+            assert np.allclose(cg[-j, -i], [nx + (gc - i) + 0.5, ny + (gc - j) + 0.5], atol=1e-14)
+    # 1D, ghost region (test_grid.jl:40-48)
+    syn = P.synthetic
+    xfg = syn.cell_faces(nx, 2, 0.0, float(nx), interior=False)
+    assert np.allclose(xfg[2:-2], xf, atol=1e-14) and np.allclose(xfg[:2], [-2, -1], atol=1e-14) and np.allclose(xfg[-2:], [11, 12], atol=1e-14)
+    xcg = syn.cell_centers(nx, 2, 0.0, float(nx), interior=False)
+    assert np.allclose(xcg[:2], [-1.5, -0.5], atol=1e-14) and np.allclose(xcg[-2:], [10.5, 11.5], atol=1e-14)
+    # inner_cells (grid.jl:213-220; test_for_each_inner_cell_2d.jl)
+    assert P.inner_cells(g, P.XDIR) == (nx, ny) and P.inner_cells(g, P.XDIR, 1) == (nx + 2, ny)
+    assert P.inner_cells(g, P.YDIR, 1) == (nx, ny + 2)
