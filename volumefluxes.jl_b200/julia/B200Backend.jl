@@ -23,6 +23,13 @@ struct B200Backend{T} <: Backend
 end
 make_b200_backend(::Type{T}=Float64; strict=false, fused=true, device=0) where {T} = B200Backend{T}(T, strict, fused, device)
 name(::B200Backend) = "B200"
+# backends/buffer.jl:23,29-31: the generic fallbacks `convert_to_backend(backend, array) = array` and
+# `create_buffer(backend, nvar, size) = zeros(backend.realtype, ...)` apply to this backend unchanged, i.e. bathymetry,
+# infiltration factor and `new_state` stay ordinary host arrays (the library owns all device memory and copies what
+# it is handed).  `ConservedSystem(...)` (system.jl:37-53) still allocates its two face volumes and the wavespeed plane
+# through them -- host memory this backend never touches; a maintainer who minds the 7 words per cell can give
+# `create_volume(::B200Backend, grid, equation)` a lazily allocated variant.
+# get_available_backends() (kernel_abstractions.jl:45-55): push `make_b200_backend()` when `dlopen(libswe)` succeeds.
 
 # mirror of swe_b200_config (include/swe_b200.h); field order and types must match exactly
 struct SweB200Config
