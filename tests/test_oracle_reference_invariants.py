@@ -197,6 +197,26 @@ def test_rain_functions_and_run(O):
     assert w.max() == pytest.approx(0.015 + 1.0, abs=1e-12) and w.min() == pytest.approx(0.015 + 1.0, abs=1e-12)
 
 
+# ---- test_compute_flux_2d.jl:27-77: gc = 1, 32 x 16, Pure SWE, NoReconstruction: fluxes and wave speeds finite ----
+def test_compute_flux_2d_smoke(O):
+    syn = cases.synthetic()
+    nx, ny = 32, 16
+    x = syn.cell_centers(nx, 1, 0.0, 1.0)
+    y = syn.cell_centers(ny, 1, 0.0, 1.0)
+    w = np.exp(-(((x[None, :] - 0.5) ** 2 + (y[:, None] - 0.5) ** 2) / 0.01)) + 1.5
+    case = dict(dim=2, nx=nx, ny=ny, gc=1, bc="periodic", pure=True, recon="none", stepper="fe", cfl=0.25)
+    s = O.OracleSim(case)
+    s.set_state_interior(w, np.zeros_like(w), np.zeros_like(w))
+    s.zero(1)
+    ms = s.add_time_derivative(0, 1, 0.0)
+    out = s.get_state_full(1)
+    assert np.all(np.isfinite(out)) and np.all(np.isfinite(s.get_wavespeeds())) and all(np.isfinite(ms)) and min(ms) > 0
+    assert np.max(np.abs(out[1])) > 0 and np.max(np.abs(out[2])) > 0       # the hump drives momentum in both directions
+    for _ in range(5):
+        s.step()
+    assert np.all(np.isfinite(s.get_state_full()))
+
+
 # ---- test_rain.jl:98-146: FunctionalRain (constant / time-dependent / spatial closures) ----------------
 def test_functional_rain(O):
     case, st = cases.rain_case(10, 0.01)
