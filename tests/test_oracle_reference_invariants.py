@@ -197,6 +197,31 @@ def test_rain_functions_and_run(O):
     assert w.max() == pytest.approx(0.015 + 1.0, abs=1e-12) and w.min() == pytest.approx(0.015 + 1.0, abs=1e-12)
 
 
+# ---- test_timesteppers.jl:26-58, 76-99: the stepper algebra integrates y' = y with order 1 (FE) / 2 (RK2) ----------
+@pytest.mark.parametrize("stepper,order", [("fe", 1.0), ("rk2", 2.0)])
+def test_timestepper_order(O, stepper, order):
+    """run_without_simulator of the reference test: do_substep! with a stub system whose time derivative is the state
+    itself (output += state), driven through the oracle's own substep pieces (zero / axpy / rk_average / rotate =
+    rungekutta.jl:26-52, forwardeuler.jl:28-47, simulator.jl:172-175)."""
+    s = O.OracleSim(dict(dim=2, nx=4, ny=4, gc=2, pure=True, recon="none", stepper=stepper))
+    nsub = 2 if stepper == "rk2" else 1
+    errors, dts = [], 1.0 / 2.0 ** np.arange(4, 11)
+    for dt in dts:
+        s.set_state_full(np.ones((3, s.Ny, s.Nx)), 0)
+        for _ in range(int(round(1.0 / dt))):
+            for k in range(nsub):
+                s.set_state_full(s.get_state_full(k), k + 1)      # out = 0; out += L(S[k]) with L(y) = y
+                s.axpy(k + 1, k, dt)                              # out = S[k] + dt * out
+                if k == 1:
+                    s.rk_average(2, 0)                            # out = (S[1] + out) / 2
+            s.rotate()
+        y = s.get_state_full(0)
+        assert np.all(y == y[0, 0, 0])
+        errors.append(abs(float(y[0, 0, 0]) - np.e))
+    slope = np.polyfit(np.log(dts), np.log(errors), 1)[0]
+    assert slope == pytest.approx(order, abs=0.05)
+
+
 # ---- test_compute_flux_2d.jl:27-77: gc = 1, 32 x 16, Pure SWE, NoReconstruction: fluxes and wave speeds finite ----
 def test_compute_flux_2d_smoke(O):
     syn = cases.synthetic()
