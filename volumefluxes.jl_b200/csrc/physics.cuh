@@ -233,13 +233,24 @@ template <class C>
 __device__ __forceinline__ C minmod3(C a, C b, C c) {
     return mx((C)0, mn(mn(a, b), c)) + mn((C)0, mx(mx(a, b), c));
 }
-template <class P>
+// ALT (fast Float64 only): the same value with 3 compare-and-selects instead of 6 --
+//   sign(f) * min(theta * min(|f|,|b|), (|f|+|b|)/2) if f and b have the same sign, else 0
+// (theta * x is monotone, so theta * min = min of the products; |f|+|b| = |f+b| for equal signs).  Measured on the
+// Float64 stage kernels: stage 1 -4.6 %, stage 2 +6.6 % (register allocation), so only stage 1 selects it.
+template <class P, bool ALT = false>
 __device__ __forceinline__ typename P::C minmod_slope(typename P::S l, typename P::S c, typename P::S r,
                                                       typename P::C theta) {
     using S = typename P::S;
     using C = typename P::C;
     S f = r - c;
     S b = c - l;
+    if constexpr (ALT && !P::strict && sizeof(C) == 8) {
+        const C af = ab(f), abb = ab(b);
+        const C m1 = af < abb ? af : abb;
+        const C t = theta * m1, cen = (C)0.5 * (af + abb);
+        const C m2 = t < cen ? t : cen;
+        return (f * b > (C)0) ? cps(m2, (C)f) : (C)0;
+    }
     C cen = (C)(f + b) * (C)0.5;   // (f+b)/2.0 : the S-precision sum, then an exact halving
     return minmod3<C>(theta * f, cen, theta * b);
 }
@@ -247,7 +258,7 @@ __device__ __forceinline__ typename P::C minmod_slope(typename P::S l, typename 
 // ---- reconstruction of one cell: face values (h, hu, hv) on its left/right face --------------------
 // linearreconstruction.jl:73-100 (practical SWE: w-slope clamp, then subtract face bathymetry);
 // :44-56 for Pure; noreconstruction.jl:30-46 for RECON == 0.
-template <class P, int RECON, bool PURE>
+template <class P, int RECON, bool PURE, bool ALT = false>
 __device__ __forceinline__ void recon_cell(const Par<typename P::C>& p, const typename P::S l[3],
                                            const typename P::S c[3], const typename P::S r[3],
                                            typename P::C Bl, typename P::C Br, typename P::C Bc,
@@ -261,7 +272,7 @@ __device__ __forceinline__ void recon_cell(const Par<typename P::C>& p, const ty
     } else {
         C s[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) s[k] = minmod_slope<P>(l[k], c[k], r[k], p.theta);
+        for (int k = 0; k < 3; ++k) s[k] = minmod_slope<P, ALT>(l[k], c[k], r[k], p.theta);
         const C half = (C)0.5;
         if constexpr (!PURE) {
             const S w = c[0];
