@@ -159,7 +159,10 @@ def build_case(n: int, dtype: str, ny=None, config: int = 5):
         return cases.terrain_case(n=n, dtype=dtype, level=1.0)
     if kind == "urban":
         return cases.urban_case(n=n, dtype=dtype, level=1.0)
-    return cases.lake_case(n=n, ny=ny, dtype=dtype, level=0.0)
+    return cases.lake_case(n=n, ny=ny, dtype=dtype, level=LAKE_LEVEL)
+
+
+LAKE_LEVEL = 0.0     # --level: still-water level of the config-5 lake (0 = the bench line, 54 % wet; 60 = every cell wet)
 
 
 def wet_fraction(case, state):
@@ -217,7 +220,7 @@ def workload_config(args, n, wet):
                 "l2": "3 volumes of %.0f MB" % (3 * 3 * (n + 4) ** 2 * np.dtype(args.dtype).itemsize / 1e6)
                       + (" fit the 126 MB L2: an L2 flush (256 MB memset) runs between timed steps" if args.flush_l2 else "")}
     return {"workload": f"configs[4]: {n}x{n} {args.dtype} synthetic bathymetry (separable 5-octave hills, seed 1234), "
-                        f"lake at level 0 + Gaussian hump ({wet:.0%} of cells wet), WallBC, LinearReconstruction(1.2), "
+                        f"lake at level {LAKE_LEVEL:g} + Gaussian hump ({wet:.0%} of cells wet), WallBC, LinearReconstruction(1.2), "
                         "CentralUpwind, SourceTermBottom, ImplicitFriction(bh2021), RungeKutta2, cfl 0.25, "
                         "depth_cutoff = kappa = 1e-3",
             "grid": [n, n], "arithmetic": "fast" if not args.strict else "strict",
@@ -432,12 +435,16 @@ def main():
     ap.add_argument("--ny", type=int, default=None, help="N = 1 only: rows of a non-square grid (strip-shaped tuning runs)")
     ap.add_argument("--equal-strips", action="store_true", dest="equal_strips",
                     help="N > 1: equal-height y-strips instead of the cost-balanced partition")
+    ap.add_argument("--level", type=float, default=0.0,
+                    help="config 5: still-water level of the lake (0 = the bench line, ~54 %% of the cells wet; 60 floods every cell)")
     ap.add_argument("--dry-cost", type=float, default=0.6, dest="dry_cost",
                     help="cost of a dry cell relative to a wet one in the strip balancing model")
     args = ap.parse_args()
     args.n = args.n or CONFIGS[args.config][1]
     args.dtype = args.dtype or CONFIGS[args.config][2]
     args.flush_l2 = 3 * 3 * (args.n + 4) * ((args.ny or args.n) + 4) * np.dtype(args.dtype).itemsize < 4 * 126e6
+    global LAKE_LEVEL
+    LAKE_LEVEL = args.level
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -152,6 +152,14 @@ int swe_b200_enumerate_inner_cells(swe_b200_handle* h, int dir, int ghostcells,
 int swe_b200_enumerate_ghost_cells(swe_b200_handle* h, int dir, int64_t* out /*[n][2]*/,
                                    int64_t* count);
 
+/* The same index spaces for a bare grid -- no simulator handle: this is what the backend-level kernel surface
+ * `for_each_cell(f, backend, grid, y...)`, `for_each_inner_cell(f, backend, grid, direction, y...; ghostcells)`,
+ * `for_each_ghost_cell(f, backend, grid, direction, y...)` (backends/kernel_abstractions.jl:73, 83, 129) binds.
+ * kind 0 = cells, 1 = inner cells, 2 = ghost cells; nx, ny = interior cells, gc = grid.ghostcells; dir 0/1;
+ * `ghostcells` is the keyword of for_each_inner_cell (ignored otherwise).  Errors: swe_b200_last_error(NULL). */
+int swe_b200_enumerate_grid(int kind, int nx, int ny, int gc, int dir, int ghostcells, int device,
+                            int64_t* out, int64_t* count);
+
 /* ---- device-side reductions for callbacks ---------------------------------------------------------
  * Callbacks that only need scalars (examples/example_tools.jl:86-90 TotalWaterVolume:
  * sum(collect(current_interior_state(sim).h) .- B_cell); driven by IntervalWriter, callbacks.jl:40-55)
@@ -202,6 +210,30 @@ int swe_b200_run_steps_timed(swe_b200_handle* h, int64_t n, double maximum_times
                              swe_b200_timing* out);
 /* total number of kernels this handle has launched so far */
 int swe_b200_launch_count(swe_b200_handle* h, int64_t* count);
+
+/* Which kernel family serves step / run_steps / simulate_to_time on this handle (>= 0; < 0 = error).  The
+ * reference has one code path per operator (system.jl:62-75); this backend has several, selected at create()
+ * from the configuration -- a host can log it, a test can assert it:
+ *   PER_OPERATOR  one kernel per reference operator (ShallowWaterEquationsPure, gc != 2, cfg.fused == 0)
+ *   FUSED_GENERIC the one-column fused stage kernels (strict policies; anything the packed kernels refuse)
+ *   FUSED_X2      the packed two-column Float32 stage kernels (the performance path of the bench line)
+ *   FUSED_D1      the Float64 ring / persistent-warp stage kernels */
+enum { SWE_B200_FAMILY_PER_OPERATOR = 0, SWE_B200_FAMILY_FUSED_GENERIC = 1, SWE_B200_FAMILY_FUSED_X2 = 2,
+       SWE_B200_FAMILY_FUSED_D1 = 3 };
+int swe_b200_kernel_family(swe_b200_handle* h);
+
+/* Per-cell comparison, ON THE DEVICE, of the states (buffer `buffer`) of two handles with the same grid, dtype
+ * and device -- e.g. the fast-arithmetic handle against the strict (bit-faithful) one at sizes where the CPU
+ * oracle cannot run and a D2H copy of both states would dominate.  Interior cells only (SURVEY 8c protocol):
+ *   out[0..2] = max |a - b| of w, hu, hv      out[3..5] = max |b| of w, hu, hv   (b = `other`)
+ *   out[6] = number of cells whose wet flag (w - B_cell >= depth_cutoff) differs
+ *   out[7], out[8] = wet cells of a, of b      out[9] = cells holding a NaN in either state
+ *   out[10..12] = number of cells whose |a - b| of w, hu, hv exceeds thresholds[0..2] (absolute values; a second
+ *                 call with thresholds = tolerance x out[3..5] of the first counts the cells over a relative
+ *                 tolerance); 0 when thresholds == NULL */
+#define SWE_B200_COMPARE_SLOTS 13
+int swe_b200_compare_states(swe_b200_handle* h, swe_b200_handle* other, int buffer, const double* thresholds,
+                            double out[SWE_B200_COMPARE_SLOTS]);
 
 #ifdef __cplusplus
 }

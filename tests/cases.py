@@ -81,6 +81,40 @@ def swashes412_analytic(x, t, g=9.81, hl=0.005, x0=5.0):
     return h, u
 
 
+def swashes411_analytic(x, t, g=9.81, hl=0.005, hr=0.001, cm=0.1578324867, x0=5.0):
+    """test/swashes.jl:131-156 (dam break on a wet domain, Stoker's solution; cm from swashes.jl:54)."""
+    c = np.sqrt(g * hl)
+    xA = x0 - t * c
+    xB = x0 + t * (2 * c - 3 * cm)
+    xC = x0 + t * (2 * cm ** 2 * (c - cm)) / (cm ** 2 - g * hr)
+    rar_h = (4.0 / (9.0 * g)) * (c - (x - x0) / (2 * t)) ** 2
+    rar_u = (2.0 / 3.0) * ((x - x0) / t + c)
+    h = np.where(x < xA, hl, np.where(x < xB, rar_h, np.where(x < xC, cm ** 2 / g, hr)))
+    u = np.where(x < xA, 0.0, np.where(x < xB, rar_u, np.where(x < xC, 2 * (c - cm), 0.0)))
+    return h, u
+
+
+def swashes422b(n=100, dtype="float64", t=0.0, a=1.0, L=4.0, g=9.81, h0=0.1, eta=0.5, stepper="rk2"):
+    """SWASHES 4.2.2.b, 2D planar surface in a paraboloid (test/swashes.jl:106-119, 260-289, 303-308): bathymetry at
+    the corners, the analytic state at time t on the interior (w = max(plane, B_cell), hu = u h, hv = v h).
+    Returns (case, state, rotation period 2 pi / omega)."""
+    syn = synthetic()
+    omega = np.sqrt(2 * g * h0) / a
+    xf = syn.cell_faces(n, 2, 0.0, L, interior=False)
+    X, Y = np.meshgrid(xf, xf)
+    B = -h0 * (1 - ((X - L / 2) ** 2 + (Y - L / 2) ** 2) / a ** 2)
+    xc = syn.cell_centers(n, 2, 0.0, L)
+    XC, YC = np.meshgrid(xc, xc)
+    Bc = syn.cell_average(B)[2:-2, 2:-2]
+    cs, sn = np.cos(omega * t), np.sin(omega * t)
+    w = np.maximum((eta * h0 / a ** 2) * (2 * (XC - L / 2) * cs + 2 * (YC - L / 2) * sn - eta), Bc)
+    h = w - Bc
+    state = (w, -eta * omega * sn * h, eta * omega * cs * h)
+    case = dict(dim=2, dtype=dtype, nx=n, ny=n, gc=2, bc="wall", extent=[0.0, L, 0.0, L], depth_cutoff=1e-5,
+                kappa=1e-5, theta=1.2, cfl=0.25, stepper=stepper, recon="linear", B=B.astype(dtype), bottom_source=True, g=g)
+    return case, tuple(np.ascontiguousarray(s, dtype=dtype) for s in state), 2 * np.pi / omega
+
+
 # ------------------------------------------------------------------------------------------
 # lake at rest (test/test_lake_at_rest_2d.jl:28-119)
 # ------------------------------------------------------------------------------------------

@@ -14,6 +14,10 @@ Two kinds of fixtures:
    numbers; they freeze the restatement (any later change of the oracle or of the seeded generators shows up
    as a golden mismatch) and give the GPU tests a committed vector to compare with at run time on the GPU box,
    where /root/reference does not exist.
+
+Closing the gap on a Julia-equipped machine (see tests/golden/dump_reference.jl):
+  python tests/golden/make_golden.py --export-inputs DIR ; julia dump_reference.jl DIR ;
+  python tests/golden/make_golden.py --import-reference DIR      # -> reference_trajectories.npz, picked up by test_golden.py
 """
 from __future__ import annotations
 
@@ -107,7 +111,51 @@ def run_case(oracle, name, dtype):
     return full[:, 2:-2, 2:-2].copy(), np.array(dts, dtype=np.float64), o.t, sha(inputs)
 
 
+def export_inputs(dirname):
+    """parameters + raw little-endian input arrays of every golden case, for tests/golden/dump_reference.jl"""
+    d = Path(dirname)
+    d.mkdir(parents=True, exist_ok=True)
+    for name in GOLDEN_CASES:
+        for dtype in ("float64", "float32"):
+            case, state = GOLDEN_CASES[name](dtype)
+            key = f"{name}.{dtype}"
+            B = case.get("B")
+            inf = case.get("infiltration")
+            params = {"dtype": dtype, "nx": case["nx"], "ny": case["ny"], "gc": case.get("gc", 2), "bc": case.get("bc", "periodic"),
+                      "extent": [float(x) for x in case.get("extent", [0.0, 1.0, 0.0, 1.0])],
+                      "depth_cutoff": case.get("depth_cutoff", 1e-5), "kappa": case.get("kappa", 1e-5),
+                      "theta": case.get("theta", 1.2), "cfl": case.get("cfl", 0.25), "stepper": case.get("stepper", "rk2"),
+                      "recon": case.get("recon", "linear"), "friction": case.get("friction"),
+                      "bottom_source": bool(case.get("bottom_source", False)), "rain": case.get("rain"),
+                      "infiltration": None if inf is None else ("horton" if isinstance(inf, dict) else float(inf)),
+                      "maximum_timestep": case.get("maximum_timestep"), "has_B": isinstance(B, np.ndarray), "nsteps": NSTEPS}
+            (d / f"{key}.json").write_text(json.dumps(params, indent=1) + "\n")
+            for nm, a in zip(("w", "hu", "hv"), state):
+                np.ascontiguousarray(a, dtype=dtype).tofile(d / f"{key}.{nm}.bin")    # (ny, nx) C-order == Julia (nx, ny)
+            if isinstance(B, np.ndarray):
+                np.ascontiguousarray(B, dtype=dtype).tofile(d / f"{key}.B.bin")
+    print("exported", len(list(d.glob("*.json"))), "cases to", d)
+
+
+def import_reference(dirname):
+    """packs the outputs of dump_reference.jl into tests/golden/reference_trajectories.npz"""
+    d = Path(dirname)
+    out = {}
+    for pj in sorted(d.glob("*.json")):
+        key = pj.name[:-5]
+        p = json.loads(pj.read_text())
+        st = np.fromfile(d / f"{key}.ref_state.bin", dtype=p["dtype"]).reshape(3, p["ny"], p["nx"])
+        out[key + ".state"] = st
+        out[key + ".dt"] = np.fromfile(d / f"{key}.ref_dt.bin", dtype=np.float64)
+    np.savez_compressed(HERE / "reference_trajectories.npz", **out)
+    print("wrote reference_trajectories.npz with", len(out) // 2, "cases")
+
+
 def main():
+    if len(sys.argv) == 3 and sys.argv[1] == "--export-inputs":
+        return export_inputs(sys.argv[2])
+    if len(sys.argv) == 3 and sys.argv[1] == "--import-reference":
+        return import_reference(sys.argv[2])
     oracle = cases.load_oracle()
     out = {}
     meta = {"nsteps": NSTEPS, "cases": {}}

@@ -130,8 +130,13 @@ def test_x2_kernels_sass_has_packed_fp32_and_async_copies():
             kernels[name] = []
         elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             kernels[name].append(line)
-    k1 = "_ZN3swe2x210k_stage_x2ILi1ELb1ELi1ELi0ELb0EEEvNS0_5Args2E"
-    k2 = "_ZN3swe2x210k_stage_x2ILi1ELb1ELi2ELi1ELb0EEEvNS0_5Args2E"
+    # (the kernels live in a per-translation-unit inline namespace, tu_namespace.h: match on the template arguments)
+    def find(args):
+        hits = [k for k in kernels if "k_stage_x2" in k and args in k]
+        assert len(hits) == 1, f"k_stage_x2<{args}> not (uniquely) in engine_fast.o: {hits}"
+        return hits[0]
+    k1 = find("ILi1ELb1ELi1ELi0ELb0EE")     # <RECON=1, HASB=true, STAGE=1, FRIC=0, FACTOR=false>
+    k2 = find("ILi1ELb1ELi2ELi1ELb0EE")     # <RECON=1, HASB=true, STAGE=2, FRIC=1, FACTOR=false>
     for k in (k1, k2):
         assert k in kernels, f"{k} not in engine_fast.o"
         body = "\n".join(kernels[k])

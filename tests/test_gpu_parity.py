@@ -264,7 +264,7 @@ def test_gaussian_pure_unfused(P, oracle):
 
 
 @pytest.mark.parametrize("strict,fused", [(False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("kind,T", [("412", 4.0)])
+@pytest.mark.parametrize("kind,T", [("412", 4.0), ("411", 6.0)])
 def test_swashes_x_equals_y_bitwise(P, oracle, kind, T, strict, fused):
     """test_swashes.jl:317-328 on the CUDA path: the x-run and the y-run are bitwise mirror images,
     with equal dt; in strict mode they also equal the oracle's 1D run bitwise."""
@@ -291,7 +291,7 @@ def test_swashes_x_equals_y_bitwise(P, oracle, kind, T, strict, fused):
     else:
         assert cases.rel_linf(wx[1, :], h1) <= 1e-9
     xc = cases.synthetic().cell_centers(nx, 2, 0.0, 10.0)
-    h_ref, _ = cases.swashes412_analytic(xc, T)
+    h_ref, _ = (cases.swashes412_analytic if kind == "412" else cases.swashes411_analytic)(xc, T)
     assert np.mean(np.abs(wx[1, :] - h_ref)) < 4e-5
 
 

@@ -76,10 +76,13 @@ SYMBOLS = {
     "swe_b200_enumerate_cells": (_i, [_vp, _vp, _pi64]),
     "swe_b200_enumerate_inner_cells": (_i, [_vp, _i, _i, _vp, _pi64]),
     "swe_b200_enumerate_ghost_cells": (_i, [_vp, _i, _vp, _pi64]),
+    "swe_b200_enumerate_grid": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _pi64]),
     "swe_b200_get_ipc_handle": (_i, [_vp, _vp]),
     "swe_b200_open_peers": (_i, [_vp, _vp]),
     "swe_b200_run_steps_timed": (_i, [_vp, _i64, _d, C.POINTER(Timing)]),
     "swe_b200_launch_count": (_i, [_vp, _pi64]),
+    "swe_b200_kernel_family": (_i, [_vp]),
+    "swe_b200_compare_states": (_i, [_vp, _vp, _i, _pd, _pd]),
 }
 
 

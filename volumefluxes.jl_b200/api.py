@@ -598,6 +598,34 @@ class Simulator:
         self._check(_lib.lib().swe_b200_launch_count(self._h, C.byref(n)))
         return n.value
 
+    KERNEL_FAMILIES = {0: "per-operator", 1: "fused-generic", 2: "fused-x2", 3: "fused-d1"}
+
+    def kernel_family(self) -> str:
+        """which kernel family serves step / run_steps / simulate_to_time on this handle (swe_b200_kernel_family)"""
+        rc = _lib.lib().swe_b200_kernel_family(self._h)
+        if rc < 0:
+            self._check(rc)
+        return self.KERNEL_FAMILIES[rc]
+
+    def compare_states(self, other, buffer=0, tol=None):
+        """Per-cell comparison with another simulator's state ON THE DEVICE (same grid / dtype / device): dict with
+        the rel-L-inf errors of SURVEY 8c (w against max|w|, momenta against max(|hu|,|hv|) of `other`), the number of
+        cells whose wet flag differs, the wet-cell counts and -- with `tol` -- the number of cells per field whose
+        error exceeds tol x the field's scale."""
+        L = _lib.lib()
+        out = (C.c_double * 13)()
+        self._check(L.swe_b200_compare_states(self._h, other._h, int(buffer), None, out))
+        o = list(out)
+        dw = max(o[3], 1e-300)
+        dm = max(o[4], o[5], 1e-300)
+        res = dict(rel_linf=[o[0] / dw, o[1] / dm, o[2] / dm], max_abs_diff=o[0:3], max_abs_ref=o[3:6],
+                   mask_mismatch=int(o[6]), wet=int(o[7]), wet_other=int(o[8]), nan_cells=int(o[9]))
+        if tol is not None:
+            thr = (C.c_double * 3)(tol * dw, tol * dm, tol * dm)
+            self._check(L.swe_b200_compare_states(self._h, other._h, int(buffer), thr, out))
+            res["cells_over_tol"] = [int(out[10]), int(out[11]), int(out[12])]
+        return res
+
     # -- fine-grained operators ---------------------------------------------------------------------------
     def update_bc(self, buffer=0):
         self._check(_lib.lib().swe_b200_update_bc(self._h, buffer))
@@ -824,31 +852,45 @@ class TotalWaterVolume:
 
 
 # ---- the backend kernel surface ---------------------------------------------------------------------
-def _grid_probe(backend, grid) -> Simulator:
-    eq = ShallowWaterEquationsPure()
-    sys_ = ConservedSystem(backend, NoReconstruction(), CentralUpwind(eq), eq, grid)
-    return Simulator(B200Backend(backend.realtype, backend.strict, False, backend.device), sys_, ForwardEulerStepper(), grid)
+# for_each_cell(f, backend, grid, y...), for_each_inner_cell(f, backend, grid, direction, y...; ghostcells),
+# for_each_ghost_cell(f, backend, grid, direction, y...) (kernel_abstractions.jl:73, 83, 129).  A precompiled
+# backend cannot execute an arbitrary closure on the device: the index space is enumerated by a device kernel
+# (swe_b200_enumerate_grid -- no simulator needed, like the reference's signature) and `f` is applied on the host
+# to each 1-based index with the trailing arguments y...  The hot-path CALLERS of this surface (reconstruct!,
+# compute_flux!, do_substep!, update_bc!, ...) never come here: they have fused CUDA implementations.
+def _enumerate_grid(kind, backend, grid, direction=0, ghostcells=0):
+    L = _lib.lib()
+    n = C.c_int64()
+    args = (kind, grid.nx, grid.ny, grid.gc, int(direction), int(ghostcells), backend.device)
+    rc = L.swe_b200_enumerate_grid(*args, None, C.byref(n))
+    if rc:
+        _raise(rc)
+    out = np.empty((n.value, 6 if kind == 1 else 2), dtype=np.int64)
+    if n.value:
+        rc = L.swe_b200_enumerate_grid(*args, _ptr(out), C.byref(n))
+        if rc:
+            _raise(rc)
+    return out
 
 
-def for_each_cell(f, backend, grid):
-    """for_each_cell(f, backend, grid) (kernel_abstractions.jl:123-131).  A precompiled backend cannot
-    execute an arbitrary closure on the device: the index space is enumerated by a device kernel and `f`
-    is applied on the host to each 1-based index (i, j)."""
-    for i, j in _grid_probe(backend, grid).enumerate("cells"):
-        f((int(i), int(j)))
+def for_each_cell(f, backend, grid, *y):
+    """for_each_cell(f, backend, grid, y...) (kernel_abstractions.jl:123-131): f(index, y...), 1-based (i, j)."""
+    for i, j in _enumerate_grid(0, backend, grid):
+        f((int(i), int(j)), *y)
 
 
-def for_each_inner_cell(f, backend, grid, direction, ghostcells=None):
-    """for_each_inner_cell(f, backend, grid, direction; ghostcells) (kernel_abstractions.jl:66-75):
-    f(left, middle, right) with 1-based index pairs."""
-    for r in _grid_probe(backend, grid).enumerate("inner", direction, ghostcells):
-        f((int(r[0]), int(r[1])), (int(r[2]), int(r[3])), (int(r[4]), int(r[5])))
+def for_each_inner_cell(f, backend, grid, direction, *y, ghostcells=None):
+    """for_each_inner_cell(f, backend, grid, direction, y...; ghostcells=grid.ghostcells[direction])
+    (kernel_abstractions.jl:66-75): f(left, middle, right, y...) with 1-based index pairs."""
+    g = grid.gc if ghostcells is None else int(ghostcells)
+    for r in _enumerate_grid(1, backend, grid, direction, g):
+        f((int(r[0]), int(r[1])), (int(r[2]), int(r[3])), (int(r[4]), int(r[5])), *y)
 
 
-def for_each_ghost_cell(f, backend, grid, direction):
-    """for_each_ghost_cell(f, backend, grid, direction) (kernel_abstractions.jl:77-85)."""
-    for i, j in _grid_probe(backend, grid).enumerate("ghost", direction):
-        f((int(i), int(j)))
+def for_each_ghost_cell(f, backend, grid, direction, *y):
+    """for_each_ghost_cell(f, backend, grid, direction, y...) (kernel_abstractions.jl:77-85): f(ghostcell, y...)."""
+    for i, j in _enumerate_grid(2, backend, grid, direction):
+        f((int(i), int(j)), *y)
 
 
 # ---- convenience for tests / bench: build a Simulator from a case dict (tests/cases.py) -----------------

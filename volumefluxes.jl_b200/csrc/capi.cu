@@ -98,8 +98,34 @@ int swe_b200_post_proc_substep(swe_b200_handle* h, int b) { FWD(post_proc_subste
 int swe_b200_enumerate_cells(swe_b200_handle* h, int64_t* out, int64_t* n) { FWD(enumerate(0, 0, 0, out, n)); }
 int swe_b200_enumerate_inner_cells(swe_b200_handle* h, int dir, int g, int64_t* out, int64_t* n) { FWD(enumerate(1, dir, g, out, n)); }
 int swe_b200_enumerate_ghost_cells(swe_b200_handle* h, int dir, int64_t* out, int64_t* n) { FWD(enumerate(2, dir, 0, out, n)); }
+int swe_b200_enumerate_grid(int kind, int nx, int ny, int gc, int dir, int ghostcells, int device, int64_t* out, int64_t* n) {
+    if (!n || kind < 0 || kind > 2 || dir < 0 || dir > 1 || nx < 1 || ny < 1 || gc < 0 || ghostcells < 0) return SWE_B200_EINVAL;
+    std::string err;
+    int rc = swe::enumerate_grid(kind, nx, ny, gc, dir, ghostcells, device, out, n, err);
+    if (rc) g_create_error = err;
+    return rc;
+}
 int swe_b200_get_ipc_handle(swe_b200_handle* h, void* p) { FWD(get_ipc_handle(p)); }
 int swe_b200_open_peers(swe_b200_handle* h, const void* p) { FWD(open_peers(p)); }
+int swe_b200_kernel_family(swe_b200_handle* h) { H_OR_FAIL(h); return h->e->kernel_family(); }
+int swe_b200_compare_states(swe_b200_handle* h, swe_b200_handle* other, int buffer, const double* thresholds,
+                            double out[SWE_B200_COMPARE_SLOTS]) {
+    H_OR_FAIL(h);
+    H_OR_FAIL(other);
+    int a[4], b[4];
+    h->e->dims(a);
+    other->e->dims(b);
+    if (a[0] != b[0] || a[1] != b[1] || a[2] != b[2] || a[3] != b[3] || h->e->device() != other->e->device()) {
+        h->last = h->e->err = "compare_states: the two handles must have the same grid, dtype and device";
+        return SWE_B200_EINVAL;
+    }
+    if (buffer < 0 || buffer > 2) return SWE_B200_EINVAL;
+    cudaSetDevice(h->e->device());
+    int rc = other->e->sync();                        // the other handle works on its own stream
+    if (rc) return fail(other, rc);
+    rc = h->e->compare(other->e->state_ptr(buffer), buffer, thresholds, out);
+    return rc ? fail(h, rc) : rc;
+}
 int swe_b200_launch_count(swe_b200_handle* h, int64_t* c) { H_OR_FAIL(h); *c = h->e->launch_count(); return SWE_B200_OK; }
 
 }  // extern "C"

@@ -39,8 +39,17 @@ struct Engine {
     virtual int get_ipc_handle(void* handle64) = 0;
     virtual int open_peers(const void* all_handles64) = 0;
     virtual int64_t launch_count() const = 0;
+    virtual int kernel_family() const = 0;
+    virtual const void* state_ptr(int buffer) const = 0;
+    virtual int elem_bytes() const = 0;
+    virtual void dims(int out[4]) const = 0;          // nx, ny, gc, dtype
+    virtual int compare(const void* other_state, int buffer, const double* thresholds, double out[SWE_B200_COMPARE_SLOTS]) = 0;
     virtual int device() const = 0;
 };
+
+// iteration spaces of the kernel surface for a bare grid (no simulator): swe_b200_enumerate_grid
+int enumerate_grid(int kind, int nx, int ny, int gc, int dir, int ghostcells, int device, int64_t* out, int64_t* count,
+                   std::string& err);
 
 // factories, one per translation unit / arithmetic policy family
 Engine* make_engine_fast(const swe_b200_config& cfg, std::string& err);

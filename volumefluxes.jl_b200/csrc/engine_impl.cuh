@@ -17,7 +17,7 @@
 #include "kernels_fused.cuh"
 #include "kernels_fused_x2.cuh"
 
-namespace swe {
+SWE_NS_BEGIN
 
 #define SWE_CUDA(call)                                                                          \
     do {                                                                                        \
@@ -65,6 +65,7 @@ public:
     RainTable rt;
     InfilPar ip;
     bool fused_ok = false;
+    bool d1_ok = false;     // Float64 fast policy: the ring / persistent-warp stage kernels (kernels_fused_d1.cuh)
     // ---- multi-GPU exchange window: the three volumes + the mailbox live in ONE allocation ----
     char* slab = nullptr;
     size_t vol_bytes = 0, mbox_offset = 0, slab_bytes = 0;
@@ -398,7 +399,8 @@ public:
             SWE_CUDA(cudaMemcpy2DAsync(dst[k], sizeof(S) * cfg.nx, U + (size_t)k * plane + (size_t)gc * Nx + gc, sizeof(S) * Nx,
                                        sizeof(S) * cfg.nx, cfg.ny, cudaMemcpyDeviceToHost, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
-        return check();
+        int rc = check_timeout();
+        return rc ? rc : check();
     }
     int set_state_full(int b, const void* data) override {
         if (bad_buffer(b)) return SWE_B200_EINVAL;
@@ -410,12 +412,12 @@ public:
         if (bad_buffer(b)) return SWE_B200_EINVAL;
         SWE_CUDA(cudaMemcpyAsync(data, vol[cur[b]], sizeof(S) * plane * 3, cudaMemcpyDeviceToHost, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
-        return SWE_B200_OK;
+        return check_timeout();
     }
     int pull_ctl() {
         SWE_CUDA(cudaMemcpyAsync(h_ctl, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
-        return SWE_B200_OK;
+        return check_timeout();      // multi-rank: a wait that gave up means halo rows / CFL maxima are stale
     }
     int set_time(double t, double dt) override {
         int rc = pull_ctl();
@@ -523,7 +525,8 @@ public:
         launches += 2;
         SWE_CUDA(cudaMemcpyAsync(out, diag_buf + (size_t)nb * DIAG_SLOTS, sizeof(double) * DIAG_SLOTS, cudaMemcpyDeviceToHost, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
-        return check();
+        int rc = check_timeout();
+        return rc ? rc : check();
     }
     // system.jl:62-75 on device buffers; the per-direction max lands in ctl->maxspeed_bits
     void launch_time_derivative(S* out, const S* state) {
@@ -825,6 +828,8 @@ public:
             ev_stage.clear();
             cudaEventDestroy(t0);
             cudaEventDestroy(t1);
+            int rc2 = check_timeout();
+            if (rc2) return rc2;
         }
         return check();
     }
@@ -836,18 +841,27 @@ public:
         rc = pull_ctl();
         if (rc) return rc;
         const long long n0 = h_ctl->nsteps;
-        int batch = 1;
+        int batch = 1, stalled = 0;
+        int result = SWE_B200_OK;
         while (h_ctl->t < t_end) {
+            const double t_before = h_ctl->t;
             for (int s = 0; s < batch; ++s) one_step(0.0, 1, match_endtime, t_end, maximum_timestep, 1);
             rc = check();
             if (rc) return rc;
             rc = pull_ctl();
             if (rc) return rc;
-            if (std::isnan(h_ctl->t) || std::isnan(h_ctl->dt)) { err = "NaN time step"; break; }
+            // the reference would loop forever on these (simulator.jl:199-210); an ABI call must come back
+            if (std::isnan(h_ctl->t) || std::isnan(h_ctl->dt)) { err = "simulate_to_time: NaN time step (the state blew up)"; result = SWE_B200_EDOMAIN; break; }
+            stalled = h_ctl->t == t_before ? stalled + 1 : 0;
+            if (stalled >= 3) {      // >= 1 + 2 + 4 steps without any progress in t: dt == 0 (e.g. an infinite wave speed)
+                err = "simulate_to_time: the time step is 0, t does not advance (infinite wave speed?)";
+                result = SWE_B200_EDOMAIN;
+                break;
+            }
             if (batch < 32) batch *= 2;
         }
         if (nsteps) *nsteps = h_ctl->nsteps - n0;
-        return SWE_B200_OK;
+        return result;
     }
 
     int enumerate(int kind, int dir, int g, int64_t* out, int64_t* count) override {
@@ -920,8 +934,41 @@ public:
         unsigned long long t = 0;
         SWE_CUDA(cudaMemcpyAsync(&t, &mbox->timeout, sizeof(t), cudaMemcpyDeviceToHost, stream));
         SWE_CUDA(cudaStreamSynchronize(stream));
-        if (t) { err = "multi-GPU exchange timed out waiting for a neighbour"; return SWE_B200_ECUDA; }
+        if (t) {
+            err = "multi-GPU exchange timed out waiting for a neighbour: halo rows / CFL maxima are stale, the state of "
+                  "this handle is invalid";
+            return SWE_B200_ECUDA;
+        }
         return SWE_B200_OK;
+    }
+    // which kernel family serves step / run_steps / simulate_to_time on this handle (swe_b200_kernel_family)
+    int kernel_family() const override {
+        if (!fused_ok) return SWE_B200_FAMILY_PER_OPERATOR;
+        if (x2_ok) return SWE_B200_FAMILY_FUSED_X2;
+        if (d1_ok) return SWE_B200_FAMILY_FUSED_D1;
+        return SWE_B200_FAMILY_FUSED_GENERIC;
+    }
+    const void* state_ptr(int b) const override { return vol[cur[b]]; }
+    int elem_bytes() const override { return (int)sizeof(S); }
+    void dims(int out[4]) const override { out[0] = cfg.nx; out[1] = cfg.ny; out[2] = gc; out[3] = cfg.dtype; }
+    // per-cell comparison of this handle's state with another handle's (same grid, same dtype, same device) on the
+    // device: parity checks at sizes where a D2H copy + numpy diff of both states would dominate the test
+    int compare(const void* other_state, int b, const double* thresholds, double out[SWE_B200_COMPARE_SLOTS]) override {
+        static_assert(CMP_SLOTS == SWE_B200_COMPARE_SLOTS, "compare slots");
+        CmpThr thr{};
+        if (thresholds) { thr.on = 1; for (int k = 0; k < 3; ++k) thr.v[k] = thresholds[k]; }
+        if (bad_buffer(b)) return SWE_B200_EINVAL;
+        const int nb = 148 * 4;
+        double* buf = nullptr;
+        SWE_CUDA(cudaMalloc(&buf, sizeof(double) * CMP_SLOTS * (nb + 1)));
+        k_cmp_partial<P><<<nb, 256, 0, stream>>>(vol[cur[b]], (const S*)other_state, bathy(), cfg.nx, cfg.ny, Nx, gc, plane,
+                                                 cfg.depth_cutoff, thr, buf);
+        k_cmp_final<<<1, 256, 0, stream>>>(buf, nb, buf + (size_t)nb * CMP_SLOTS);
+        launches += 2;
+        SWE_CUDA(cudaMemcpyAsync(out, buf + (size_t)nb * CMP_SLOTS, sizeof(double) * CMP_SLOTS, cudaMemcpyDeviceToHost, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(buf);
+        return check();
     }
     int64_t launch_count() const override { return launches; }
     int device() const override { return cfg.device; }
@@ -939,4 +986,4 @@ Engine* make_engine_t(const swe_b200_config& cfg, std::string& err) {
     return e;
 }
 
-}  // namespace swe
+SWE_NS_END  // namespace swe

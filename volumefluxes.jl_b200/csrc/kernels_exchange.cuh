@@ -9,7 +9,7 @@
 #pragma once
 #include "kernels_unfused.cuh"
 
-namespace swe {
+SWE_NS_BEGIN
 
 constexpr int MAX_RANKS = 8;
 
@@ -22,6 +22,7 @@ struct Mailbox {
 
 __device__ __forceinline__ bool spin_until(volatile unsigned long long* p, unsigned long long want, Mailbox* mb) {
     const long long t0 = clock64();
+    if (*(volatile unsigned long long*)&mb->timeout) return false;     // an earlier wait gave up: do not spin again
     while (*p < want) {
         __nanosleep(64);
         if (clock64() - t0 > 6000000000ll) {   // ~3 s at 2 GHz
@@ -161,4 +162,4 @@ __global__ void k_halo_push(const PushArgs<S> a) {
     }
 }
 
-}  // namespace swe
+SWE_NS_END  // namespace swe

@@ -22,7 +22,7 @@
 #pragma once
 #include "kernels_unfused.cuh"
 
-namespace swe {
+SWE_NS_BEGIN
 
 constexpr int FUSED_VW = 28;     // valid (output) columns per warp
 constexpr int FUSED_WPB = 4;     // warps per block
@@ -365,10 +365,11 @@ __global__ void k_bc_advance(S* d, int Nx, int Ny, long long plane, int gc, int 
         const bool phys = dir == 0 ? true : (side == 0 ? ylo_phys != 0 : yhi_phys != 0);
         if (phys) {
             S* base = d + (size_t)k * plane + (size_t)pp * sp;
-            const S sgn = (bc == SWE_B200_BC_WALL && k == normal) ? (S)-1 : (S)1;
+            const bool flip = bc == SWE_B200_BC_WALL && k == normal;
             const int a = side == 0 ? g : N - 1 - g;
             bool f;
-            base[(size_t)a * sa] = sgn * base[(size_t)bc_source(a, N, gc, bc, true, true, f) * sa];
+            const S v = base[(size_t)bc_source(a, N, gc, bc, true, true, f) * sa];
+            base[(size_t)a * sa] = flip ? -v : v;          // a copy or a sign flip: exact for subnormals too
         }
     }
     if (t == 0 && advance) {
@@ -382,4 +383,4 @@ __global__ void k_bc_advance(S* d, int Nx, int Ny, long long plane, int gc, int 
     }
 }
 
-}  // namespace swe
+SWE_NS_END  // namespace swe

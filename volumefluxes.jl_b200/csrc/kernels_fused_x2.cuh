@@ -23,7 +23,7 @@
 
 #include "kernels_fused.cuh"
 
-namespace swe {
+SWE_NS_BEGIN
 namespace x2 {
 
 typedef float2 f2;
@@ -40,17 +40,32 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c
 __device__ __forceinline__ f2 sub(f2 a, f2 b) { return __ffma2_rn(b, sp(-1.0f), a); }   // a - b
 __device__ __forceinline__ f2 swp(f2 a) { return make_float2(a.y, a.x); }
 __device__ __forceinline__ f2 neg(f2 a) { return make_float2(-a.x, -a.y); }
+// X2_ACCURATE=1: correctly rounded reciprocal / square root / libm cbrt instead of the MUFU approximations
+// (<= 1-2 ulp each).  An A/B switch for the parity study (profiles/r02_parity.md): it separates the approximation
+// error of these three from the conditioning of the wet/dry scheme.
+#ifndef X2_ACCURATE
+#define X2_ACCURATE 0
+#endif
 __device__ __forceinline__ float rcp_a(float x) {
+#if X2_ACCURATE
+    return __frcp_rn(x);
+#endif
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float sqrt_a(float x) {
+#if X2_ACCURATE
+    return __fsqrt_rn(x);
+#endif
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float cbrt_a(float x) {   // sign(x) * 2^(log2|x| / 3): two MUFU
+#if X2_ACCURATE
+    return cbrtf(x);
+#endif
     float l, e;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fabsf(x)));
     l *= 0.33333334f;
@@ -724,4 +739,4 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
 }
 
 }  // namespace x2
-}  // namespace swe
+SWE_NS_END  // namespace swe

@@ -8,7 +8,7 @@
 
 #include "physics.cuh"
 
-namespace swe {
+SWE_NS_BEGIN
 
 // Device-resident control block: dt, t and the CFL reduction never visit the host inside a step
 // (the reference syncs 4x per step: numericalflux.jl:32).
@@ -330,9 +330,9 @@ __global__ void k_bc(S* d, int Nx, int Ny, long long plane, int gc, int bc, int 
                 if (lo_phys) A(g) = dir == 0 ? A(2 * gc - g + 1) : A(N + g - 2 * gc);
                 if (hi_phys) A(N - (gc - g)) = A(N - g + 1);
             } else {
-                const S sgn = k == normal ? (S)-1 : (S)1;
-                if (lo_phys) A(g) = sgn * A(gc * 2 + 1 - g);
-                if (hi_phys) A(N - gc + g) = sgn * A(N - gc - g + 1);
+                const bool flip = k == normal;                 // a copy or a sign flip: exact for subnormals too
+                if (lo_phys) { const S v = A(gc * 2 + 1 - g); A(g) = flip ? -v : v; }
+                if (hi_phys) { const S v = A(N - gc - g + 1); A(N - gc + g) = flip ? -v : v; }
             }
         }
     }
@@ -393,6 +393,66 @@ static __global__ void __launch_bounds__(256) k_diag_final(const double* partial
     diag_block_reduce(v, out);
 }
 
+// ---- per-cell comparison of two states on the same grid (swe_b200_compare_states): parity checks at sizes where
+// copying both states to the host would dominate.  slots: 0..2 max|a-b| of w, hu, hv over the interior,
+// 3..5 max|b| of w, hu, hv, 6 number of cells whose wet flag (w - B_cell >= depth_cutoff) differs, 7 / 8 wet cells of
+// a / b, 9 number of cells with any NaN, 10..12 number of cells whose |a-b| of w, hu, hv exceeds thr[0..2] (absolute
+// thresholds; 0 when thr is not given).
+constexpr int CMP_SLOTS = 13;
+struct CmpThr { double v[3]; int on; };
+__device__ __forceinline__ void cmp_combine(double a[CMP_SLOTS], const double b[CMP_SLOTS]) {
+    for (int s = 0; s < 6; ++s) a[s] = fmax(a[s], b[s]);
+    for (int s = 6; s < CMP_SLOTS; ++s) a[s] += b[s];
+}
+__device__ __forceinline__ void cmp_block_reduce(double v[CMP_SLOTS], double* out) {
+    __shared__ double sh[8][CMP_SLOTS];
+    for (int o = 16; o > 0; o >>= 1) {
+        double w[CMP_SLOTS];
+        for (int s = 0; s < CMP_SLOTS; ++s) w[s] = __shfl_down_sync(0xffffffffu, v[s], o);
+        cmp_combine(v, w);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) for (int s = 0; s < CMP_SLOTS; ++s) sh[warp][s] = v[s];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) cmp_combine(v, sh[w]);
+        for (int s = 0; s < CMP_SLOTS; ++s) out[s] = v[s];
+    }
+}
+template <class P>
+__global__ void __launch_bounds__(256) k_cmp_partial(const typename P::S* A, const typename P::S* Bv, Bathy<P> bt, int nx,
+                                                     int ny, int Nx, int gc, long long plane, double cutoff, CmpThr thr,
+                                                     double* partial) {
+    using S = typename P::S;
+    double v[CMP_SLOTS];
+    for (int s = 0; s < CMP_SLOTS; ++s) v[s] = 0.0;
+    const long long n = (long long)nx * ny;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q % nx) + gc, j = (int)(q / nx) + gc;
+        const size_t at = (size_t)j * Nx + i;
+        const S bc = (S)bt.cell(i, j);
+        double c[CMP_SLOTS];
+        bool nan = false;
+        for (int k = 0; k < 3; ++k) {
+            const double x = (double)A[at + k * plane], y = (double)Bv[at + k * plane];
+            nan = nan || x != x || y != y;
+            c[k] = fabs(x - y);
+            c[3 + k] = fabs(y);
+            c[10 + k] = thr.on && c[k] > thr.v[k] ? 1.0 : 0.0;
+        }
+        const bool wa = (double)(S)(A[at] - bc) >= cutoff, wb = (double)(S)(Bv[at] - bc) >= cutoff;
+        c[6] = wa != wb ? 1.0 : 0.0; c[7] = wa ? 1.0 : 0.0; c[8] = wb ? 1.0 : 0.0; c[9] = nan ? 1.0 : 0.0;
+        cmp_combine(v, c);
+    }
+    cmp_block_reduce(v, partial + (size_t)blockIdx.x * CMP_SLOTS);
+}
+static __global__ void __launch_bounds__(256) k_cmp_final(const double* partial, int nblocks, double* out) {
+    double v[CMP_SLOTS];
+    for (int s = 0; s < CMP_SLOTS; ++s) v[s] = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) cmp_combine(v, partial + (size_t)b * CMP_SLOTS);
+    cmp_block_reduce(v, out);
+}
+
 // ---- iteration spaces of the backend kernel surface (kernel_abstractions.jl:66-131, grid.jl:213-253) ------
 // kind 0: for_each_cell, 1: for_each_inner_cell(dir; ghostcells), 2: for_each_ghost_cell(dir).
 // Each work-item records the 1-based indices it would hand to the closure.
@@ -425,4 +485,4 @@ static __global__ void k_enumerate(int kind, int dir, int g, int Nx, int Ny, int
     }
 }
 
-}  // namespace swe
+SWE_NS_END  // namespace swe

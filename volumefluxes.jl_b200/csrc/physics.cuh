@@ -19,7 +19,9 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
-namespace swe {
+#include "tu_namespace.h"
+
+SWE_NS_BEGIN
 
 template <class S_, class C_, bool STRICT_>
 struct Policy {
@@ -249,7 +251,9 @@ __device__ __forceinline__ typename P::C minmod_slope(typename P::S l, typename 
         const C m1 = af < abb ? af : abb;
         const C t = theta * m1, cen = (C)0.5 * (af + abb);
         const C m2 = t < cen ? t : cen;
-        return (f * b > (C)0) ? cps(m2, (C)f) : (C)0;
+        // same strict sign, tested on the sign bits: a product f * b would underflow to 0 for tiny differences
+        const bool same = ((__double2hiint((double)f) ^ __double2hiint((double)b)) >= 0) && m1 > (C)0;
+        return same ? cps(m2, (C)f) : (C)0;
     }
     C cen = (C)(f + b) * (C)0.5;   // (f+b)/2.0 : the S-precision sum, then an exact halving
     return minmod3<C>(theta * f, cen, theta * b);
@@ -365,4 +369,4 @@ __device__ __forceinline__ int bc_source(int a, int N, int gc, int bc, bool lo_p
     return a;
 }
 
-}  // namespace swe
+SWE_NS_END  // namespace swe
