@@ -27,7 +27,12 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
+
+
+def package():
+    """the product package (its directory name contains a dot: imported through importlib, see __graft_entry__)"""
+    from __graft_entry__ import _load_package
+    return _load_package()
 
 METRIC = "2D SWE cell-updates/s"
 UNIT = "cell-updates/s"
@@ -151,61 +156,75 @@ CONFIGS = {
 
 
 def build_case(n: int, dtype: str, ny=None, config: int = 5):
-    import cases
+    W = package().workloads
     kind = CONFIGS[config][0]
     if kind == "swashes":
-        return cases.swashes_dambreak_2d(n=n, dtype=dtype)
+        return W.swashes_dambreak_2d(n=n, dtype=dtype)
     if kind == "terrain":
-        return cases.terrain_case(n=n, dtype=dtype, level=1.0)
+        return W.terrain_case(n=n, dtype=dtype, level=1.0)
     if kind == "urban":
-        return cases.urban_case(n=n, dtype=dtype, level=1.0)
-    return cases.lake_case(n=n, ny=ny, dtype=dtype, level=LAKE_LEVEL)
+        return W.urban_case(n=n, dtype=dtype, level=1.0)
+    return W.lake_case(n=n, ny=ny, dtype=dtype, level=LAKE_LEVEL)
 
 
 LAKE_LEVEL = 0.0     # --level: still-water level of the config-5 lake (0 = the bench line, 54 % wet; 60 = every cell wet)
 
 
 def wet_fraction(case, state):
-    import cases
     if not isinstance(case.get("B"), np.ndarray):
         return float(np.mean(state[0].astype(np.float64) >= case["depth_cutoff"]))
-    Bc = cases.synthetic().cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
+    Bc = package().synthetic.cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
     return float(np.mean(state[0].astype(np.float64) - Bc >= case["depth_cutoff"]))
 
 
 def wet_fraction_rows(case, state):
     """wet fraction of every interior row of a strip (input of the strip balancing cost model)"""
-    import cases
-    Bc = cases.synthetic().cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
+    Bc = package().synthetic.cell_average(np.asarray(case["B"]))[2:-2, 2:-2]
     return np.mean(state[0].astype(np.float64) - Bc >= case["depth_cutoff"], axis=1)
 
 
 def run_reference(args, rank):
-    """The reference's CPU algorithm (oracle restatement: the Julia package cannot run here, see
-    DESIGN.md) on the host cores, on a bounded crop of the same workload."""
+    """The reference's CPU algorithm (oracle restatement: the Julia package cannot run here) on the
+    host cores.  Every step is a bounded sample of the workload: config 5 -> a FULL-WIDTH band of `--cpu-rows` rows
+    from the middle of the same 16384-wide domain (same row length, same generator, streaming working set far beyond
+    the CPU caches: 16 words per cell), other configs -> an `--cpu-n`^2 instance of the same generator."""
     if rank != 0:
         return
     from oracle import oracle
     threads = oracle.set_threads(os.cpu_count() or 1)
-    n = args.cpu_n
-    case, state = build_case(n, args.dtype, config=args.config)
+    if args.config == 5:
+        n, rows = args.n, min(args.cpu_rows, args.n)
+        case, state, y0 = package().workloads.lake_strip_case(n, 0, 1, dtype=args.dtype, level=LAKE_LEVEL,
+                                                              rows=((args.n - rows) // 2, rows))
+        case["extent"] = [0.0, float(n), 0.0, float(rows)]          # a stand-alone domain with the workload's dx = dy = 1
+        shape = [n, rows]
+        what = f"full-width band: rows {y0}..{y0 + rows} of the {n}x{n} domain"
+    else:
+        n = args.cpu_n
+        case, state = build_case(n, args.dtype, config=args.config)
+        shape = [n, n]
+        what = f"{n}x{n} instance of the same generator"
     o = oracle.OracleSim(case)
     o.set_state_interior(*state)
+    mts = case.get("maximum_timestep") or float("inf")
     for _ in range(args.warmup):
-        o.step()
+        o.step(mts)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.step()
+        o.step(mts)
     dt = time.perf_counter() - t0
-    value = n * n * args.steps / dt
-    sample = f"{n}x{n} crop of the same synthetic terrain/IC generator, {args.steps} RK2 steps, {threads} OpenMP threads"
+    cells = shape[0] * shape[1]
+    value = cells * args.steps / dt
+    sample = (f"{what} ({shape[0]}x{shape[1]} cells per step), {args.steps} RK2 steps, {threads} OpenMP threads; "
+              "C++ restatement of the reference algorithm (oracle/), not the Julia package")
+    cfg = workload_config(args, args.n, wet_fraction(case, state))
+    cfg["reference_sample_grid"] = shape      # the grid this arm actually steps; `grid` is the workload it samples
+    cfg["parallelism"] = f"{threads} host threads (OpenMP)"
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64",
-        "data": "synthetic",
-        # same workload as our arm (config 5 at --n); every step of this arm is a bounded sample of it (see `sample`)
-        "config": dict(workload_config(args, args.n, wet_fraction(case, state)), sampled_grid=[n, n]),
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -222,16 +241,18 @@ def workload_config(args, n, wet):
     return {"workload": f"configs[4]: {n}x{n} {args.dtype} synthetic bathymetry (separable 5-octave hills, seed 1234), "
                         f"lake at level {LAKE_LEVEL:g} + Gaussian hump ({wet:.0%} of cells wet), WallBC, LinearReconstruction(1.2), "
                         "CentralUpwind, SourceTermBottom, ImplicitFriction(bh2021), RungeKutta2, cfl 0.25, "
-                        "depth_cutoff = kappa = 1e-3",
+                        "depth_cutoff = kappa = 1e-3 (SURVEY 8d sketched 1e-5 and lake level 5 on a 40 m terrain; this "
+                        "generator's hills are +-8 m, and 1e-5 is 10 Float32 ulps of w: workloads.py)",
             "grid": [n, n], "arithmetic": "fast" if not args.strict else "strict",
-            "parallelism": f"y-strips x{args.gpus}" if args.gpus > 1 else "single GPU",
+            "parallelism": (f"y-strips x{args.gpus}; halo rows + CFL maxima by peer stores over NVLink from the library's "
+                            "own kernels (torch.distributed NCCL group only for set-up and barriers)") if args.gpus > 1 else "single GPU",
             "l2": "working set (state 3 x 3 planes + B, > 10 GB at 16384^2) far exceeds the 126 MB L2; no flush needed"}
 
 
 def run_ours(args, rank, world):
-    import cases
     import torch
-    P = cases.load_package()
+    P = package()
+    W = P.workloads
     n = args.n
     local = int(os.environ.get("LOCAL_RANK", 0))
     dist = None
@@ -241,43 +262,72 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.perf_counter()
     balance = None
+    strip = None
+
+    def gather_rows(vec, sizes):
+        """all-gather of per-row vectors of unequal length -> one global per-row vector"""
+        buf = torch.zeros(max(sizes), dtype=torch.float64, device="cuda")
+        buf[:len(vec)] = torch.from_numpy(np.asarray(vec, dtype=np.float64)).cuda()
+        allv = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(allv, buf)
+        return np.concatenate([allv[r][:sizes[r]].cpu().numpy() for r in range(world)])
+
+    def make_strip(y0, rows):
+        case, state, y0 = W.lake_strip_case(n, rank, world, dtype=args.dtype, level=LAKE_LEVEL, rows=(y0, rows))
+        pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in state]
+        s = P.multigpu.StripSimulator(case, [p.numpy() for p in pinned], rank, world, n, y0, P.multigpu.torch_all_gather,
+                                      device=local, strict=args.strict)
+        return case, state, pinned, s
+
     if world > 1:
-        case, state, y0 = cases.lake_strip_case(n, rank, world, dtype=args.dtype)
-        rows = case["ny"]
+        offs, sizes = P.multigpu.partition_rows(n, world)
+        case, state, y0 = W.lake_strip_case(n, rank, world, dtype=args.dtype, level=LAKE_LEVEL)
         if not args.equal_strips:
-            # load-balanced strips: every rank measures the wet fraction of the rows of its equal-height strip,
-            # the per-row vector is all-gathered, and every rank derives the same cost-equalising cuts
-            # (multigpu.partition_rows with row_cost); the strip is then generated again for its final rows.
-            wr = wet_fraction_rows(case, state)
-            sizes_eq = P.multigpu.partition_rows(n, world)[1]
-            buf = torch.zeros(max(sizes_eq), dtype=torch.float64, device="cuda")
-            buf[:rows] = torch.from_numpy(wr).cuda()
-            allw = [torch.zeros_like(buf) for _ in range(world)]
-            dist.all_gather(allw, buf)
-            wet_rows = np.concatenate([allw[r][:sizes_eq[r]].cpu().numpy() for r in range(world)])
-            offs, sizes = P.multigpu.partition_rows(n, world, P.multigpu.row_cost_from_wet_fraction(wet_rows, args.dry_cost))
-            balance = {"rows_per_rank": sizes, "dry_cost": args.dry_cost}
-            if (offs[rank], sizes[rank]) != (y0, rows):
-                case, state, y0 = cases.lake_strip_case(n, rank, world, dtype=args.dtype, rows=(offs[rank], sizes[rank]))
-                rows = case["ny"]
+            # Cost-balanced strips: every rank waits for the slowest one at the CFL all-gather, so the strips are cut
+            # by work, not by rows.  Pass 1: a model (a dry cell costs `dry_cost` of a wet one) on the per-row wet
+            # fractions.  Pass 2: the model is rescaled per rank by the MEASURED stage-kernel time of a short run on the
+            # pass-1 strips (clock / power differences between the GPUs and everything the model misses), and the rows
+            # are cut again.  All ranks derive the same cuts from the same all-gathered vectors.
+            model = P.multigpu.row_cost_from_wet_fraction(gather_rows(wet_fraction_rows(case, state), sizes), args.dry_cost)
+            offs, sizes = P.multigpu.partition_rows(n, world, model)
+            balance = {"dry_cost": args.dry_cost, "rows_model": list(sizes)}
+            if args.rebalance:
+                case, state, pinned, strip = make_strip(offs[rank], sizes[rank])
+                strip.sim.run_steps(3)
+                tm0 = strip.sim.run_steps_timed(args.rebalance)
+                mine = torch.tensor([tm0["stage_kernel_ms"]], dtype=torch.float64, device="cuda")
+                allt = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allt, mine)
+                measured = np.array([float(x.item()) for x in allt])
+                new_offs, new_sizes = P.multigpu.partition_rows(
+                    n, world, P.multigpu.rescale_cost_by_measured(model, offs, sizes, measured))
+                balance.update(rows_measured=list(new_sizes),
+                               stage_ms_before=[round(float(m) / args.rebalance, 4) for m in measured])
+                if list(new_sizes) != list(sizes):
+                    del strip, pinned
+                    strip = None
+                    offs, sizes = new_offs, new_sizes
+            balance["rows_per_rank"] = list(sizes)
+        if strip is None:
+            case, state, pinned, strip = make_strip(offs[rank], sizes[rank])
+        y0, rows = offs[rank], sizes[rank]
+        sim = strip.sim
     else:
         case, state = build_case(n, args.dtype, ny=args.ny, config=args.config)
         y0, rows = 0, (args.ny or n)
+        pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in state]
     wet = wet_fraction(case, state)
     # pinned host buffers for the end-to-end leg
-    pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in state]
     host_in = [p.numpy() for p in pinned]
     out_pinned = [torch.empty_like(p).pin_memory() for p in pinned]
     if world > 1:
-        strip = P.multigpu.StripSimulator(case, host_in, rank, world, n, y0, P.multigpu.torch_all_gather,
-                                          device=local, strict=args.strict)
-        sim = strip.sim
         w = torch.tensor([wet * rows], dtype=torch.float64, device="cuda")
         dist.all_reduce(w)
         wet = float(w.item()) / n
     else:
         sim = P.simulator_from_case(case, strict=args.strict, fused=not args.unfused, device=local)
         sim.set_state_interior(*host_in)
+    family = sim.kernel_family()
     t_setup = time.perf_counter() - t_setup
 
     def barrier():
@@ -361,14 +411,20 @@ def run_ours(args, rank, world):
     k2_ms = tm["stage2_ms"] / ns2
     k1_ms = tm["stage1_ms"] / ns2
     achieved = W2 * itemsize * cells_local / (k2_ms * 1e-3) / 1e9
+    # dram__bytes_read + write of ONE K2 launch from an `ncu --set full` capture of exactly this launch shape
+    # (profiles/traffic.json, keyed by dtype, grid and config); null when no capture exists for it (N > 1 strips, --ny,
+    # --level, other sizes): a number measured on another launch would not describe this one
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
-    if tf.exists():
+    if tf.exists() and world == 1 and not args.ny and LAKE_LEVEL == 0.0 and not args.strict and not args.unfused:
         try:
-            traffic = json.loads(tf.read_text()).get(f"k_stage2_{args.dtype}_{n}")
+            traffic = json.loads(tf.read_text()).get(f"k_stage2_{args.dtype}_{n}" + ("" if args.config == 5 else f"_config{args.config}"))
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": ("x2::k_stage_x2<RECON=1, HASB=1, STAGE=2, FRIC=1> (K2: RK2 stage 2, fused)" if args.config == 5 else "x2::k_stage_x2<..., STAGE=2> (K2: RK2 stage 2, fused)") if args.dtype == "float32" and not args.strict and not args.unfused else "k_stage<..., STAGE=2> (K2, generic fused kernel)", "achieved": achieved, "peak": peak,
+    kname = {"fused-x2": "x2::k_stage_x2<" + ("RECON=1, HASB=1, STAGE=2, FRIC=1" if args.config == 5 else "..., STAGE=2") + "> (K2: RK2 stage 2, fused, packed Float32)",
+             "fused-d1": "d1::k_stage_d1<..., STAGE=2> (K2: RK2 stage 2, fused, Float64 rings)",
+             "fused-generic": "k_stage<..., STAGE=2> (K2, generic fused kernel)"}.get(family, family)
+    roofline = {"bound": "hbm", "kernel": kname, "kernel_family": family, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": W2 * itemsize * cells_local,
                 "avg_launch_ms": k2_ms, "per": "GPU (rank 0's strip)" if world > 1 else "GPU",
@@ -382,7 +438,7 @@ def run_ours(args, rank, world):
         from oracle import oracle
         oracle.set_threads(1)
         cn = args.cpu_n
-        ccase, cstate = build_case(cn, args.dtype, config=args.config)
+        ccase, cstate = build_case(cn, args.dtype, config=args.config)     # (config 5 at --level, like the GPU arm)
         o = oracle.OracleSim(ccase)
         o.set_state_interior(*cstate)
         o.step()
@@ -392,7 +448,7 @@ def run_ours(args, rank, world):
             o.step()
         cdt = time.perf_counter() - t0
         cpu = {"value": cn * cn * csteps / cdt, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{cn}x{cn} crop of the same generator, {csteps} RK2 steps, scalar oracle restatement "
+               "sample": f"{cn}x{cn} instance of the same generator, {csteps} RK2 steps, scalar oracle restatement "
                          "(the Julia reference cannot run here: no julia binary)"}
 
     out = {
@@ -428,6 +484,10 @@ def main():
     ap.add_argument("--n", type=int, default=None)
     ap.add_argument("--dtype", default=None, choices=["float32", "float64"])
     ap.add_argument("--cpu-n", type=int, default=1024, dest="cpu_n")
+    ap.add_argument("--cpu-rows", type=int, default=1024, dest="cpu_rows",
+                    help="--impl reference, config 5: rows of the full-width band each CPU step processes")
+    ap.add_argument("--rebalance", type=int, default=4,
+                    help="N > 1: timed steps of the short run whose measured per-rank stage-kernel times re-cut the strips (0: model only)")
     ap.add_argument("--cpu-steps", type=int, default=30, dest="cpu_steps", help="RK2 steps of the cpu_baseline sample")
     ap.add_argument("--strict", action="store_true")
     ap.add_argument("--unfused", action="store_true")

@@ -102,8 +102,8 @@ def full(out, sizes):
               "at these sizes it stands in for the reference.  `sens` = strict run from a +-1 ulp perturbed initial state "
               "against the strict run from the original one.\n\n"
               "`cells > tol` = number of cells whose error exceeds the north_star tolerance x the field's scale (fast / perturbed strict).\n\n"
-              "| config | grid | steps | fast vs strict (w / hu / hv) | strict 1-ulp sens | err / max(tol, sens) | mask mismatches fast / perturbed (of wet cells) | cells > tol, fast (w / hu / hv) | cells > tol, perturbed strict | dt rel diff |\n"
-              "|---|---|---|---|---|---|---|---|---|---|\n")
+              "| config | grid | steps | fast vs strict (w / hu / hv) | strict 1-ulp sens | err / max(tol, sens) | mask mismatches fast / perturbed (of wet cells) | cells > tol, fast (w / hu / hv) | cells > tol, perturbed strict | cells > 10 tol, fast | cells > 10 tol, perturbed strict | dt rel diff |\n"
+              "|---|---|---|---|---|---|---|---|---|---|---|---|\n")
     for cfg, n in sizes:
         label, build, checkpoints = FULL[cfg]
         t0 = time.perf_counter()
@@ -125,11 +125,14 @@ def full(out, sizes):
             done = n_steps
             c = fast.compare_states(strict, tol=tol)
             cp = pert.compare_states(strict, tol=tol)
+            c10 = fast.compare_states(strict, tol=10 * tol)["cells_over_tol"]
+            cp10 = pert.compare_states(strict, tol=10 * tol)["cells_over_tol"]
             ratio = max(e / max(tol, sn) for e, sn in zip(c["rel_linf"], cp["rel_linf"]))
             ddt = abs(fast.dt - strict.dt) / strict.dt
             out.write(f"| {label} ({fast.kernel_family()}) | {n}x{n} {dtype} | {n_steps} | {fmt(c['rel_linf'])} | {fmt(cp['rel_linf'])} | "
                       f"{ratio:.2f} | {c['mask_mismatch']} / {cp['mask_mismatch']} (of {c['wet_other']}) | "
-                      f"{' / '.join(map(str, c['cells_over_tol']))} | {' / '.join(map(str, cp['cells_over_tol']))} | {ddt:.1e} |\n")
+                      f"{' / '.join(map(str, c['cells_over_tol']))} | {' / '.join(map(str, cp['cells_over_tol']))} | "
+                      f"{' / '.join(map(str, c10))} | {' / '.join(map(str, cp10))} | {ddt:.1e} |\n")
             out.flush()
             assert c["nan_cells"] == 0
         print(f"config {cfg} at {n}: {time.perf_counter() - t0:.1f} s", file=sys.stderr)

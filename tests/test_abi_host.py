@@ -111,6 +111,26 @@ def test_cost_balanced_partition(pkg):
         mg.partition_rows(83, 3, np.ones(82))
 
 
+def test_rebalance_from_measured_times(pkg):
+    """second pass of the strip balancing (bench.py): a rank that measured 20 % slower than the model predicted gets
+    fewer rows, and re-measuring with a cost that is exact leaves the cuts alone"""
+    mg = pkg.multigpu
+    ny, P = 4000, 4
+    model = np.ones(ny)
+    offs, sizes = mg.partition_rows(ny, P, model)
+    assert sizes == [1000] * 4
+    true_speed = np.array([1.0, 1.2, 1.0, 0.9])                       # per-row cost of each rank's GPU
+    measured = [sizes[r] * true_speed[r] for r in range(P)]
+    cost2 = mg.rescale_cost_by_measured(model, offs, sizes, measured)
+    offs2, sizes2 = mg.partition_rows(ny, P, cost2)
+    assert sum(sizes2) == ny and sizes2[1] < 1000 < sizes2[3]
+    # rows kept their rank's measured scale, so the predicted per-rank time is flat to within the moved rows
+    t2 = [cost2[o:o + n].sum() for o, n in zip(offs2, sizes2)]
+    assert max(t2) / min(t2) < 1.002
+    with pytest.raises(pkg.ArgumentError):
+        mg.rescale_cost_by_measured(model, offs, sizes, [1.0, 1.0, 0.0, 1.0])
+
+
 def test_x2_kernels_sass_has_packed_fp32_and_async_copies():
     """Build-quality guard (no GPU needed): the shipped Float32 stage kernels really are the sm_100a design DESIGN.md
     describes -- packed FFMA2/FMUL2/FADD2 arithmetic, LDGSTS (cp.async) ring fills, no barrier -- and ptxas reports no

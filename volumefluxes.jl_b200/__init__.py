@@ -10,3 +10,4 @@ from . import synthetic  # noqa: F401
 from .api import *  # noqa: F401,F403
 from . import api  # noqa: F401
 from . import multigpu  # noqa: F401
+from . import workloads  # noqa: F401

@@ -16,6 +16,7 @@
 #include "kernels_exchange.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_fused_x2.cuh"
+#include "kernels_fused_d1.cuh"
 
 SWE_NS_BEGIN
 
@@ -51,6 +52,7 @@ public:
     int Bp = 0;             // internal pitch of the corner bathymetry: Nx+1 rounded up to even (64-bit loads)
     bool x2_ok = false;     // Float32 fast policy: the packed two-column stage kernels (kernels_fused_x2.cuh)
     x2::Par2 par2;
+    d1::Par1 par1;
     long long plane;
     cudaStream_t stream = nullptr;
     S* vol[3] = {nullptr, nullptr, nullptr};
@@ -80,6 +82,20 @@ public:
     unsigned long long xseq = 0;        // halo exchange stamp counter (identical on all ranks)
     unsigned long long sseq = 0;        // step sequence for the CFL all-gather
     unsigned long long pending_U = 0;   // stamp of the last U exchange the next K1 must wait for
+    unsigned long long bseq = 0;        // device-side rendezvous counter (k_rank_barrier)
+    // the tail kernel of a fused step already ran ctl_begin for the NEXT step with these parameters: a following step
+    // with the same parameters starts with K1 directly (one launch less).  Anything else that touches the control
+    // block (set_time, add_time_derivative, the unfused path) clears `primed`.
+    struct BeginKey {
+        double max_dt_host, t_end, max_timestep;
+        int use_t_end, match;
+        bool operator==(const BeginKey& o) const {
+            // (bitwise-equal doubles; +inf == +inf)
+            return max_dt_host == o.max_dt_host && t_end == o.t_end && max_timestep == o.max_timestep && use_t_end == o.use_t_end && match == o.match;
+        }
+    };
+    bool primed = false;
+    BeginKey primed_key{};
     std::vector<cudaEvent_t> ev;   // per-stage-kernel timing events (timed runs only)
     std::vector<int> ev_stage;
     bool timing_on = false;
@@ -162,6 +178,7 @@ public:
         // the fused stage kernels cover the practical 2D SWE with gc == 2 and periodic / wall BCs
         fused_ok = c.fused && c.eq_kind == 0 && gc == 2 && c.bc != SWE_B200_BC_NEUMANN && c.nx >= 4 && c.ny >= 4;
         setup_x2(c);
+        setup_d1(c);
         if (multi && !fused_ok) {
             err = "y-strip decomposition needs the fused path (ShallowWaterEquations, gc == 2, periodic/wall BC)";
             return SWE_B200_EUNSUPPORTED;
@@ -211,6 +228,61 @@ public:
         // (if the item tables cannot be allocated the generic fused kernels serve the configuration)
         x2_ok = build_items(c, q.rows, 1) && build_items(c, q.rows, 2);
     }
+    // Float64 fast policy: parameters of the ring / persistent-warp kernels (kernels_fused_d1.cuh).  Same conditions as
+    // the packed Float32 kernels except the even pitch (8-byte loads of doubles are always aligned) and kappa < 1.
+    void setup_d1(const swe_b200_config& c) {
+        d1_ok = false;
+        if (!std::is_same<P, Policy<double, double, false>>::value) return;
+        const char* off = std::getenv("SWE_B200_NO_D1");
+        if (off && off[0] == '1') return;
+        if (!fused_ok || !(c.depth_cutoff >= 0) || !(c.kappa > 0)) return;
+        if (c.rain_kind == SWE_B200_RAIN_PLANE) return;      // per-cell rain: generic fused kernels
+        const int gny = c.global_ny > 0 ? c.global_ny : c.ny;
+        const double dx = (c.extent[1] - c.extent[0]) / c.nx, dy = (c.extent[3] - c.extent[2]) / gny;
+        d1::Par1& q = par1;
+        q.Nx = Nx; q.Ny = Ny; q.plane = plane; q.Bp = Bp;
+        q.bc = c.bc; q.friction = c.friction; q.bottom_source = c.has_bottom_source;
+        q.ylo_phys = par.ylo_phys; q.yhi_phys = par.yhi_phys;
+        q.rain_kind = c.rain_kind; q.infil_kind = c.infil_kind; q.infil_first = c.infil_first;
+        q.cutoff = c.depth_cutoff; q.kappa = c.kappa; q.constB = c.const_B;
+        q.theta = c.theta; q.g = c.g; q.K = 0.5 * c.rho * c.g; q.i2k = 1.0 / (2 * c.kappa); q.rho = c.rho;
+        q.nrdx = -1.0 / dx; q.nrdy = -1.0 / dy;
+        q.botx = c.has_bottom_source ? -0.25 * c.g / dx : 0.0; q.boty = c.has_bottom_source ? -0.25 * c.g / dy : 0.0;
+        q.Cz = c.Cz;
+        int rows = 126;
+        if (const char* e = std::getenv("SWE_B200_X2_ROWS")) rows = std::max(3, atoi(e) / 3 * 3);   // multiple of 3
+        d1_ok = build_items(c, rows, 1, d1::VW, d1::minb<1>() * d1::WPB) && build_items(c, rows, 2, d1::VW, d1::minb<2>() * d1::WPB);
+    }
+    template <int STAGE>
+    void launch_stage_d1(const S* U, const S* D, S* out) {
+        if constexpr (std::is_same<P, Policy<double, double, false>>::value) {
+            d1::Args1 a;
+            a.p = par1; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl; a.items = d_items[STAGE - 1];
+            a.p.nitems = n_items[STAGE - 1];
+            const int items = n_items[STAGE - 1];
+            dim3 g(std::min((items + d1::WPB - 1) / d1::WPB, 148 * d1::minb<STAGE>()));
+            dim3 b(d1::NT);
+            const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
+            const int fr = cfg.friction == SWE_B200_FRICTION_NONE ? 0 : (cfg.friction == SWE_B200_FRICTION_BH2021 ? 1 : 2);
+#define SWE_D1_LAUNCH(R, HB, F) d1::k_stage_d1<R, HB, STAGE, (STAGE == 2 ? F : 0)><<<g, b, 0, stream>>>(a)
+#define SWE_D1_FRIC(R, HB)                                                                   \
+    do {                                                                                     \
+        if (STAGE == 1 || fr == 0) SWE_D1_LAUNCH(R, HB, 0);                                  \
+        else if (fr == 1) SWE_D1_LAUNCH(R, HB, 1);                                           \
+        else SWE_D1_LAUNCH(R, HB, 2);                                                        \
+    } while (0)
+            if (B) {
+                if (lin) SWE_D1_FRIC(1, true);
+                else SWE_D1_FRIC(0, true);
+            } else {
+                if (lin) SWE_D1_FRIC(1, false);
+                else SWE_D1_FRIC(0, false);
+            }
+#undef SWE_D1_FRIC
+#undef SWE_D1_LAUNCH
+        }
+    }
+
     // Guided schedule of the persistent warps: every tile column (60 output columns) is cut into row segments;
     // most rows go into `big`-row items (the 4-row prologue amortises), the rest into three classes of ever
     // smaller items that are handed out LAST, sized so that each of the W resident warps of the stage gets about
@@ -220,9 +292,11 @@ public:
     // 1/2, 1/4, 1/4 over the small classes; measured 1-4 % slower on 2048..16384-row grids: more small items.)
     int4* d_items[2] = {nullptr, nullptr};
     int n_items[2] = {0, 0};
-    bool build_items(const swe_b200_config& c, int big, int stage) {
-        const int ntiles = (c.nx + x2::VW - 1) / x2::VW;
-        const long long W = 148LL * (stage == 2 ? x2::minb<2>() : x2::minb<1>()) * x2::WPB;
+    bool build_items(const swe_b200_config& c, int big, int stage, int vw = x2::VW,
+                     int resident_warps_per_sm = 0) {
+        if (!resident_warps_per_sm) resident_warps_per_sm = (stage == 2 ? x2::minb<2>() : x2::minb<1>()) * x2::WPB;
+        const int ntiles = (c.nx + vw - 1) / vw;
+        const long long W = 148LL * resident_warps_per_sm;
         const long long L = (long long)ntiles * c.ny;
         // small grids: a big item is at most about half of a warp's whole share of tile-rows
         if (!std::getenv("SWE_B200_X2_ROWS")) big = (int)std::min<long long>(big, std::max<long long>(12, L / W / 2 / 3 * 3));
@@ -422,6 +496,7 @@ public:
     int set_time(double t, double dt) override {
         int rc = pull_ctl();
         if (rc) return rc;
+        primed = false;
         h_ctl->t = (double)(S)t;
         h_ctl->dt = dt;
         h_ctl->dt_s = (double)(S)dt;
@@ -564,6 +639,7 @@ public:
         if (rc) return rc;
         rc = pull_ctl();
         if (rc) return rc;
+        primed = false;
         const double t_saved = h_ctl->t;
         h_ctl->t = (double)(S)t;
         SWE_CUDA(cudaMemcpyAsync(ctl, h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, stream));
@@ -603,6 +679,7 @@ public:
 
     // ---- one perform_step!, unfused: the reference's kernel sequence 1:1 (simulator.jl:145-177) ------
     void step_unfused(int advance) {
+        primed = false;
         const int nsub = cfg.stepper == SWE_B200_RK2 ? 2 : 1;
         const long long n3 = plane * 3;
         for (int s = 0; s < nsub; ++s) {
@@ -656,6 +733,7 @@ public:
         }
         const bool lin = cfg.recon == SWE_B200_RECON_LINEAR;
         if (x2_ok) launch_stage_x2<STAGE>(U, D, out);
+        else if (d1_ok) launch_stage_d1<STAGE>(U, D, out);
         else if (B) {
             if (lin) k_stage<P, 1, true, STAGE><<<g, b, 0, stream>>>(a);
             else k_stage<P, 0, true, STAGE><<<g, b, 0, stream>>>(a);
@@ -672,7 +750,7 @@ public:
     }
     // ---- multi-GPU: peer pushes of halo rows / CFL maxima (kernels_exchange.cuh) -------------------------
     // kind 0: dU rows (stamp slots 0/1), kind 2: U rows (slots 2/3); rows_only=false also publishes the speeds
-    void push_halo(const S* src, int vol_index, int kind, bool with_speed, bool rows = true, bool with_dt = false) {
+    PushArgs<S> push_args(const S* src, int vol_index, int kind, bool with_speed, bool rows, bool with_dt) {
         PushArgs<S> a{};
         a.src = src;
         a.src_plane = plane;
@@ -701,14 +779,45 @@ public:
             a.dt.nranks = cfg.nranks; a.dt.has_lo = lo_rank >= 0; a.dt.has_hi = hi_rank >= 0;
             a.dt.seq = sseq; a.dt.dU_stamp = rows ? a.stamp : 0ull;
         }
-        const long long per_side = (long long)a.rows * Nx;
-        const int bx = (int)std::max<long long>(1, std::min<long long>((per_side / 4 + 255) / 256, 8));
-        k_halo_push<S><<<dim3(bx, a.rows > 0 ? 6 : 1), 256, 0, stream>>>(a);
+        return a;
+    }
+    int push_blocks(int rows) const {
+        const long long per_side = (long long)rows * Nx;
+        return (int)std::max<long long>(1, std::min<long long>((per_side / 4 + 255) / 256, 8));
+    }
+    // kind 0: dU rows (stamp slots 0/1), kind 2: U rows (slots 2/3); rows_only=false also publishes the speeds
+    void push_halo(const S* src, int vol_index, int kind, bool with_speed, bool rows = true, bool with_dt = false) {
+        const PushArgs<S> a = push_args(src, vol_index, kind, with_speed, rows, with_dt);
+        k_halo_push<S><<<dim3(push_blocks(a.rows), a.rows > 0 ? 6 : 1), 256, 0, stream>>>(a);
         ++launches;
         if (rows && kind == 2) pending_U = a.stamp;
     }
+    // the last launch of a fused step (k_tail): ghost fill + U-row push + t += dt + the next step's ctl_begin + U-row wait
+    void launch_tail(S* next, int next_index, int advance, const BeginKey& key) {
+        TailArgs<S> a{};
+        a.d = next; a.Nx = Nx; a.Ny = Ny; a.gc = gc; a.bc = cfg.bc; a.ylo_phys = par.ylo_phys; a.yhi_phys = par.yhi_phys;
+        a.advance = advance; a.plane = plane; a.ctl = ctl;
+        a.begin.rt = rt; a.begin.ip = ip;
+        a.begin.max_dt_host = key.max_dt_host; a.begin.t_end = key.t_end; a.begin.max_timestep = key.max_timestep;
+        a.begin.use_t_end = key.use_t_end; a.begin.match_endtime = key.match; a.begin.enabled = 1;
+        const long long nthreads = (long long)((Ny - 2 * gc) + (Nx - 2 * gc)) * gc * 6;
+        a.nb_bc = (int)((nthreads + 255) / 256);
+        a.multi = peers_open ? 1 : 0;
+        int nblocks = a.nb_bc;
+        if (peers_open) {
+            a.push = push_args(next, next_index, 2, false, true, false);
+            a.nbp = push_blocks(a.push.rows);
+            a.has_lo = lo_rank >= 0; a.has_hi = hi_rank >= 0;
+            a.mb = mbox;
+            nblocks += 6 * a.nbp;
+        }
+        k_tail<S><<<nblocks, 256, 0, stream>>>(a);
+        ++launches;
+        primed = true;
+        primed_key = key;
+    }
 
-    void step_fused(int advance) {
+    void step_fused(int advance, const BeginKey& key) {
         const bool multi = peers_open;
         S* U = vol[cur[0]];
         S* D = vol[cur[1]];
@@ -722,8 +831,8 @@ public:
             push_halo(D, cur[1], 0, true, rk2, true);
         } else {
             k_ctl_dt<S><<<1, 1, 0, stream>>>(ctl, par_dx(), par_dy(), (S)cfg.cfl);
+            ++launches;
         }
-        ++launches;
         mark("dt(+push dU)");
         S* next;
         int next_index;
@@ -742,25 +851,21 @@ public:
             next_index = cur[1];
             std::swap(cur[0], cur[1]);
         }
-        // the owned boundary rows go to the neighbours first: no consumer reads the x-ghost columns of a halo
-        // row from memory (both stage kernels remap them), so the push need not wait for the ghost fill
-        if (multi) { push_halo(next, next_index, 2, false); mark("push U"); }
-        const long long nthreads = (long long)((Ny - 2 * gc) + (Nx - 2 * gc)) * gc * 6;
-        k_bc_advance<S><<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(next, Nx, Ny, plane, gc, cfg.bc, par.ylo_phys,
-                                                                    par.yhi_phys, ctl, advance);
-        ++launches;
-        mark("bc_advance");
+        launch_tail(next, next_index, advance, key);
+        mark("tail");
     }
     void one_step(double max_dt_host, int use_t_end, int match, double t_end, double max_timestep, int advance) {
-        if (peers_open && fused_ok && pending_U) {   // + wait for the neighbours' U rows of the previous exchange
+        const BeginKey key{max_dt_host, t_end, max_timestep, use_t_end, match};
+        if (peers_open && fused_ok && pending_U) {   // + wait for the neighbours' U rows of set_state_interior's exchange
             k_ctl_begin_multi<<<1, 1, 0, stream>>>(ctl, rt, ip, max_dt_host, use_t_end, match, t_end, max_timestep, mbox,
                                                    lo_rank >= 0, hi_rank >= 0, pending_U);
             pending_U = 0;
-        } else {
+            ++launches;
+        } else if (!(fused_ok && primed && primed_key == key)) {
             k_ctl_begin<<<1, 1, 0, stream>>>(ctl, rt, ip, max_dt_host, use_t_end, match, t_end, max_timestep);
+            ++launches;
         }
-        ++launches;
-        if (fused_ok) step_fused(advance);
+        if (fused_ok) step_fused(advance, key);
         else step_unfused(advance);
     }
     int prepare() {
@@ -787,6 +892,12 @@ public:
             { const char* e = std::getenv("SWE_B200_TRACE"); trace_on = e && e[0] == '1'; }
             mark("start");
             SWE_CUDA(cudaStreamSynchronize(stream));
+            if (peers_open) {      // align the GPUs: every rank's timed region starts when the last rank is ready
+                BarrierArgs ba{};
+                for (int r = 0; r < cfg.nranks; ++r) ba.mbox[r] = peer_mbox[r];
+                ba.nranks = cfg.nranks; ba.rank = cfg.rank; ba.seq = ++bseq;
+                k_rank_barrier<<<1, 32, 0, stream>>>(ba);
+            }
             SWE_CUDA(cudaEventRecord(t0, stream));
         }
         for (int64_t s = 0; s < n; ++s) one_step(inf, 0, 0, 0.0, maximum_timestep, 1);

@@ -18,6 +18,7 @@ struct Mailbox {
     unsigned long long speed_stamp[2][MAX_RANKS];  // step sequence number the slot belongs to
     unsigned long long halo_stamp[4];              // 0: dU from lower, 1: dU from upper, 2: U from lower, 3: U from upper
     unsigned long long timeout;                    // != 0: a wait gave up (reported by the host as an error)
+    unsigned long long arrive[MAX_RANKS];          // device-side rendezvous (k_rank_barrier): sequence number per rank
 };
 
 __device__ __forceinline__ bool spin_until(volatile unsigned long long* p, unsigned long long want, Mailbox* mb) {
@@ -106,10 +107,37 @@ struct PushArgs {
     DtArgs dt;                     // dt.enabled: the last block also computes the step's dt (was a launch of its own)
 };
 
+// one (side, plane) run of halo rows: blockIdx-like coordinates (bx of nbx blocks, by = side * 3 + plane).  Each
+// (side, plane) is ONE contiguous run of rows*Nx elements on both ends (the gc boundary rows are adjacent in memory),
+// copied with 16-byte peer stores when the runs are aligned.
+template <class S>
+__device__ __forceinline__ void push_rows(const PushArgs<S>& a, int bx, int nbx, int by) {
+    const long long per_side = (long long)a.rows * a.Nx;
+    if (per_side <= 0) return;
+    const int side = by / 3, k = by - 3 * side;
+    const S* src;
+    S* dst;
+    if (side == 0) {   // my lowest owned rows -> lower neighbour's top ghost rows
+        src = a.src + k * a.src_plane + (long long)a.gc * a.Nx;
+        dst = a.dst_lo ? a.dst_lo + k * a.lo_plane + (long long)(a.lo_Ny - a.gc) * a.Nx : nullptr;
+    } else {           // my highest owned rows -> upper neighbour's bottom ghost rows
+        src = a.src + k * a.src_plane + (long long)(a.Ny - 2 * a.gc) * a.Nx;
+        dst = a.dst_hi ? a.dst_hi + k * a.hi_plane : nullptr;
+    }
+    if (!dst) return;
+    const long long t = bx * (long long)blockDim.x + threadIdx.x, nt = (long long)nbx * blockDim.x;
+    constexpr int V = 16 / sizeof(S);
+    if ((((unsigned long long)src | (unsigned long long)dst) & 15ull) == 0 && per_side % V == 0) {
+        const int4* s4 = reinterpret_cast<const int4*>(src);
+        int4* d4 = reinterpret_cast<int4*>(dst);
+        for (long long q = t; q < per_side / V; q += nt) d4[q] = s4[q];
+    } else {
+        for (long long q = t; q < per_side; q += nt) dst[q] = src[q];
+    }
+}
+
 template <class S>
 __global__ void k_halo_push(const PushArgs<S> a) {
-    // blockIdx.y = side * 3 + plane: each (side, plane) is ONE contiguous run of rows*Nx elements on both ends
-    // (the gc boundary rows are adjacent in memory), copied with 16-byte peer stores when the runs are aligned.
     // The strip's CFL maxima are final when this kernel starts (stage 1 is complete): publish them before the
     // row copies so that the all-gather latency overlaps them on every rank.
     if (a.with_speed && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < a.nranks) {
@@ -120,30 +148,7 @@ __global__ void k_halo_push(const PushArgs<S> a) {
         __threadfence_system();
         *(volatile unsigned long long*)&m->speed_stamp[par][a.rank] = a.seq;
     }
-    const long long per_side = (long long)a.rows * a.Nx;
-    if (per_side > 0) {
-        const int side = blockIdx.y / 3, k = blockIdx.y - 3 * side;
-        const S* src;
-        S* dst;
-        if (side == 0) {   // my lowest owned rows -> lower neighbour's top ghost rows
-            src = a.src + k * a.src_plane + (long long)a.gc * a.Nx;
-            dst = a.dst_lo ? a.dst_lo + k * a.lo_plane + (long long)(a.lo_Ny - a.gc) * a.Nx : nullptr;
-        } else {           // my highest owned rows -> upper neighbour's bottom ghost rows
-            src = a.src + k * a.src_plane + (long long)(a.Ny - 2 * a.gc) * a.Nx;
-            dst = a.dst_hi ? a.dst_hi + k * a.hi_plane : nullptr;
-        }
-        if (dst) {
-            const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
-            constexpr int V = 16 / sizeof(S);
-            if ((((unsigned long long)src | (unsigned long long)dst) & 15ull) == 0 && per_side % V == 0) {
-                const int4* s4 = reinterpret_cast<const int4*>(src);
-                int4* d4 = reinterpret_cast<int4*>(dst);
-                for (long long q = t; q < per_side / V; q += nt) d4[q] = s4[q];
-            } else {
-                for (long long q = t; q < per_side; q += nt) dst[q] = src[q];
-            }
-        }
-    }
+    push_rows(a, blockIdx.x, gridDim.x, blockIdx.y);
     __threadfence_system();
     __syncthreads();
     __shared__ bool last;
@@ -160,6 +165,110 @@ __global__ void k_halo_push(const PushArgs<S> a) {
         __syncthreads();
         if (threadIdx.x == 0) ctl_dt_multi<S>(a.ctl_rw, a.mbox[a.rank], a.dt);
     }
+}
+
+// ---- the tail of a fused step in ONE launch (was: push U rows, k_bc_advance, next step's k_ctl_begin + U-row wait):
+//   blocks [0, nb_bc)            ghost fill of the new state (bc.jl:29-40, 81-110), both directions
+//   blocks [nb_bc, nb_bc + 6 nbp) push of the owned boundary rows of U^{n+1} into the neighbours' ghost rows
+//   block 0, thread 0             t += dt (simulator.jl:205), then the NEXT step's control set-up (ctl_begin)
+//   last block to finish          raises the neighbours' stamps, then waits for their U rows to have arrived here
+// The push need not wait for the ghost fill: no consumer reads the x-ghost columns of a halo row from memory (both
+// stage kernels remap them).
+struct BeginArgs {
+    RainTable rt;
+    InfilPar ip;
+    double max_dt_host, t_end, max_timestep;
+    int use_t_end, match_endtime, enabled;
+};
+template <class S>
+struct TailArgs {
+    S* d;
+    int Nx, Ny, gc, bc, ylo_phys, yhi_phys, advance;
+    long long plane;
+    Ctl* ctl;
+    BeginArgs begin;
+    int multi, nb_bc, nbp, has_lo, has_hi;
+    Mailbox* mb;
+    PushArgs<S> push;
+};
+template <class S>
+__device__ __forceinline__ void bc_fill(S* d, int Nx, int Ny, long long plane, int gc, int bc, int ylo_phys, int yhi_phys, long long t) {
+    // one thread per (passive index, ghost layer, side, variable): a single load + store each, so the launch is
+    // a few microseconds although the x ghosts are strided by a whole row
+    const int nxp = Ny - 2 * gc;   // passive count for x ghosts
+    const int nyp = Nx - 2 * gc;
+    const int per = gc * 2 * 3;
+    if (t >= (long long)(nxp + nyp) * per) return;
+    const int line = (int)(t / per), r = (int)(t - (long long)line * per);
+    const int k = r % 3, side = (r / 3) & 1, g = r / 6;
+    const int dir = line < nxp ? 0 : 1;
+    const int pp = (dir == 0 ? line : line - nxp) + gc;
+    const int N = dir == 0 ? Nx : Ny;
+    const size_t sa = dir == 0 ? 1 : (size_t)Nx, sp = dir == 0 ? (size_t)Nx : 1;
+    const int normal = dir == 0 ? 1 : 2;
+    const bool phys = dir == 0 ? true : (side == 0 ? ylo_phys != 0 : yhi_phys != 0);
+    if (!phys) return;
+    S* base = d + (size_t)k * plane + (size_t)pp * sp;
+    const bool flip = bc == SWE_B200_BC_WALL && k == normal;
+    const int a = side == 0 ? g : N - 1 - g;
+    bool f;
+    const S v = base[(size_t)bc_source(a, N, gc, bc, true, true, f) * sa];
+    base[(size_t)a * sa] = flip ? -v : v;          // a copy or a sign flip: exact for subnormals too
+}
+template <class S>
+__device__ __forceinline__ void ctl_advance_begin(Ctl* ctl, int advance, const BeginArgs& b) {
+    if (advance) {
+        const bool skip = ctl->use_t_end && !(ctl->t < ctl->t_end);      // a step at t == t_end is an exact no-op
+        if (!skip) {
+            S tt = (S)ctl->t;
+            tt += (S)ctl->dt_s;
+            ctl->t = (double)tt;
+            ctl->nsteps += 1;
+        }
+    }
+    if (b.enabled) ctl_begin(ctl, b.rt, b.ip, b.max_dt_host, b.use_t_end, b.match_endtime, b.t_end, b.max_timestep);
+}
+template <class S>
+__global__ void k_tail(const TailArgs<S> a) {
+    const int b = blockIdx.x;
+    if (b < a.nb_bc) {
+        bc_fill<S>(a.d, a.Nx, a.Ny, a.plane, a.gc, a.bc, a.ylo_phys, a.yhi_phys, b * (long long)blockDim.x + threadIdx.x);
+        if (b == 0 && threadIdx.x == 0) ctl_advance_begin<S>(a.ctl, a.advance, a.begin);
+    } else {
+        const int q = b - a.nb_bc;
+        push_rows(a.push, q % a.nbp, a.nbp, q / a.nbp);
+    }
+    if (!a.multi) return;
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(a.push.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *a.push.ticket = 0;
+    __threadfence_system();
+    if (threadIdx.x == 0 && a.push.flag_lo) *(volatile unsigned long long*)a.push.flag_lo = a.push.stamp;
+    if (threadIdx.x == 1 && a.push.flag_hi) *(volatile unsigned long long*)a.push.flag_hi = a.push.stamp;
+    __syncthreads();
+    // the next stage-1 kernel reads the neighbours' rows: wait for them here, at the end of the step's last launch
+    if (threadIdx.x == 0) wait_halo(a.mb, 2, a.has_lo, a.has_hi, a.push.stamp);
+}
+
+// ---- device-side rendezvous of all ranks on the handles' streams: every rank announces sequence number `seq` in
+// every peer's mailbox and waits until all have.  Used to align the GPUs before a timed region (host-side barriers
+// release the ranks up to a millisecond apart, which is 10 % of a 20-step region at N = 8).
+struct BarrierArgs {
+    Mailbox* mbox[MAX_RANKS];
+    int nranks, rank;
+    unsigned long long seq;
+};
+static __global__ void k_rank_barrier(const BarrierArgs a) {
+    if (threadIdx.x < a.nranks) {
+        __threadfence_system();
+        *(volatile unsigned long long*)&a.mbox[threadIdx.x]->arrive[a.rank] = a.seq;
+        spin_until(&a.mbox[a.rank]->arrive[threadIdx.x], a.seq, a.mbox[a.rank]);
+    }
+    __threadfence_system();
 }
 
 SWE_NS_END  // namespace swe

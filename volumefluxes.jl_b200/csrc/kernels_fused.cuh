@@ -1,6 +1,6 @@
 // kernels_fused.cuh -- the fused sm_100a stage kernels (the hot path).
 //
-// One RK2 step = K1 (stage 1) -> k_ctl_dt -> K2 (stage 2) -> k_bc_advance:
+// One RK2 step = K1 (stage 1) -> k_ctl_dt -> K2 (stage 2) -> k_tail (kernels_exchange.cuh):
 //   K1  reads U^n (3 words) + B (1)            writes dU = L(U^n) (3)      + CFL max (atomics)
 //   K2  reads U^n (3) + dU (3) + B (1)         writes U^{n+1} (3)
 // = 17 words per cell per step instead of the reference's ~183.  K2 rebuilds
@@ -341,46 +341,6 @@ __global__ void k_update_fe(Par<typename P::C> p, Bathy<P> bt, const typename P:
     substep_tail<P>(p, st, d, (C)ctl->dt, (S)ctl->dt_s, bt.cell(i, j), o);
 #pragma unroll
     for (int k = 0; k < 3; ++k) D[q + k * p.plane] = o[k];
-}
-
-// Ghost fill for both directions in one launch (x ghosts on interior rows, y ghosts on interior
-// columns: disjoint targets, interior sources), plus the t += dt bookkeeping on one thread.
-template <class S>
-__global__ void k_bc_advance(S* d, int Nx, int Ny, long long plane, int gc, int bc, int ylo_phys, int yhi_phys,
-                             Ctl* ctl, int advance) {
-    // one thread per (passive index, ghost layer, side, variable): a single load + store each, so the launch is
-    // a few microseconds although the x ghosts are strided by a whole row
-    const int nxp = Ny - 2 * gc;   // passive count for x ghosts
-    const int nyp = Nx - 2 * gc;
-    const int per = gc * 2 * 3;
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t < (long long)(nxp + nyp) * per) {
-        const int line = (int)(t / per), r = (int)(t - (long long)line * per);
-        const int k = r % 3, side = (r / 3) & 1, g = r / 6;
-        const int dir = line < nxp ? 0 : 1;
-        const int pp = (dir == 0 ? line : line - nxp) + gc;
-        const int N = dir == 0 ? Nx : Ny;
-        const size_t sa = dir == 0 ? 1 : (size_t)Nx, sp = dir == 0 ? (size_t)Nx : 1;
-        const int normal = dir == 0 ? 1 : 2;
-        const bool phys = dir == 0 ? true : (side == 0 ? ylo_phys != 0 : yhi_phys != 0);
-        if (phys) {
-            S* base = d + (size_t)k * plane + (size_t)pp * sp;
-            const bool flip = bc == SWE_B200_BC_WALL && k == normal;
-            const int a = side == 0 ? g : N - 1 - g;
-            bool f;
-            const S v = base[(size_t)bc_source(a, N, gc, bc, true, true, f) * sa];
-            base[(size_t)a * sa] = flip ? -v : v;          // a copy or a sign flip: exact for subnormals too
-        }
-    }
-    if (t == 0 && advance) {
-        const bool skip = ctl->use_t_end && !(ctl->t < ctl->t_end);
-        if (!skip) {
-            S tt = (S)ctl->t;
-            tt += (S)ctl->dt_s;
-            ctl->t = (double)tt;
-            ctl->nsteps += 1;
-        }
-    }
 }
 
 SWE_NS_END  // namespace swe

@@ -55,6 +55,22 @@ def row_cost_from_wet_fraction(wet_fraction_per_row, dry_cost: float = 0.6):
     return dry_cost + (1.0 - dry_cost) * w
 
 
+def rescale_cost_by_measured(row_cost, offsets, sizes, measured):
+    """Second pass of the strip balancing: `measured[r]` is the time rank r actually spent in its stage kernels on the
+    strip [offsets[r], offsets[r] + sizes[r]) cut with `row_cost`.  The model is rescaled strip by strip so that its
+    sum over each strip equals the measurement (GPU-to-GPU clock / power differences, item-schedule effects and
+    whatever else the model misses end up in the scale), and `partition_rows` can cut again with the result."""
+    c = np.asarray(row_cost, dtype=np.float64)
+    m = np.asarray(measured, dtype=np.float64)
+    if len(offsets) != len(sizes) or len(m) != len(sizes) or sum(sizes) != len(c) or np.any(m <= 0):
+        raise api.ArgumentError("rescale_cost_by_measured: one positive measurement per strip, strips covering all rows")
+    out = np.empty_like(c)
+    for o, n, tm in zip(offsets, sizes, m):
+        s = c[o:o + n].sum()
+        out[o:o + n] = c[o:o + n] * (tm / s if s > 0 else 1.0)
+    return out
+
+
 def strip_case(case: dict, state: Sequence[np.ndarray], rank: int, nranks: int, row_cost=None):
     """The sub-problem of `rank`: same parameters, its rows of the state, the bathymetry corner rows
     (owned rows + 2 ghost rows per side + 1) and of the infiltration factor plane."""
