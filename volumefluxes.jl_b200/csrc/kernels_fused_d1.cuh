@@ -51,12 +51,10 @@ __device__ __forceinline__ R rcp_n(R x) {                // hardware seed (~2^-2
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
-__device__ __forceinline__ R sqrt_n(R x) {               // x >= 0: rsqrt seed + two Newton steps + one correction
-    R y;
+__device__ __forceinline__ R sqrt_n(R x) {               // x >= 0: rsqrt seed (~2^-22) + one Newton step (~2^-44) on
+    R y;                                                 // 1/sqrt(x), then one correction step on sqrt(x) itself (~1 ulp)
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const R hx = 0.5 * x;
-    y = y * fma(-hx * y, y, 1.5);
-    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-0.5 * x * y, y, 1.5);
     R s = x * y;
     s = fma(fma(-s, s, x), 0.5 * y, s);
     return x > 1e-300 ? s : 0.0;                         // (rsqrt(0) = inf; the flush-to-zero seed does not see subnormals)

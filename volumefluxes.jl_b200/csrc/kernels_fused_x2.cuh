@@ -318,6 +318,17 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {     // bypasses L1 (.cg needs 16 bytes)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+// X2_FILL16=1 (experiment, profiles/r02_fill16.md): in FAST trips of warps whose 64 columns are all in range and hold no
+// remapped ghost pair, a state row is fetched as 16 x 16-byte cp.async.cg chunks per array, spread over the lanes
+// (3 copies per lane and row in stage 2 instead of 6, 1.5 instead of 3 in stage 1; no L1 allocation), at the price of
+// one __syncwarp per row (a lane then reads ring data another lane copied).  Needs 16-byte aligned rows (Nx % 4 == 0).
+#ifndef X2_FILL16
+#define X2_FILL16 0
+#endif
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -393,6 +404,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
     const int Bp = p.Bp;
     // does this warp hold x-ghost pairs (columns 0,1 or Nx-2,Nx-1)?  warp-uniform
     const bool ghost_warp = STAGE == 2 && (tile == 0 || tile * VW + 64 > Nx - 2);
+    const bool fill16 = X2_FILL16 && !ghost_warp && tile * VW + 64 <= Nx && (Nx & 3) == 0;     // warp-uniform
 
     f2 dt = sp(0.0f), czdt = sp(0.0f);
     int xs = ic;
@@ -491,6 +503,25 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
             }
         }
         pf += rowB;
+        if (X2_FILL16 && FAST && fill16) {
+            // chunk c = lane + 32 m: array c / 16 (U planes 0..2, then dU planes), 16-byte part c % 16 of the warp's 256-byte row
+            const char* gw = g - lane * 8;
+            char* const sw = smb + (tid - lane) * 8;
+            constexpr int NCH = (STAGE == 2 ? 6 : 3) * 16;
+#pragma unroll
+            for (int m = 0; m < (NCH + 31) / 32; ++m) {
+                const int c = lane + 32 * m;
+                if (NCH % 32 == 0 || c < NCH) {
+                    const int arr = c >> 4, part = c & 15;
+                    const bool isD = STAGE == 2 && arr >= 3;
+                    const int k = isD ? arr - 3 : arr;
+                    const char* src = gw + (isD ? dOff : 0) + k * planeB + part * 16;
+                    char* dst = sw + (isD ? D_OFF : ubank) + slot * U_SLOT + k * U_VAR + part * 16;
+                    cp_async16_cg(dst, src);
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             cp_async8(smU + ubank + slot * U_SLOT + k * U_VAR, g + k * planeB);
@@ -602,6 +633,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
             f2* q2 = q[(R + 2) % 3];
             // ---- arrivals: state row j+2 and corner row j+3 (rows j+3 / j+4 stay in flight) ----
             cp_async_wait_1();
+            if (X2_FILL16) __syncwarp();                  // ring data copied by other lanes of the warp becomes visible
             // (a FAST trip does not maintain the source rows: the rows it fetches are never remapped)
             const bool yflip2 = !FAST && yflip_q, remap2 = !FAST && remap_q;
             const int ys2 = remap2 ? ys_q : j + 2;
