@@ -161,12 +161,15 @@ def build_case(n: int, dtype: str, ny=None, config: int = 5):
     if kind == "swashes":
         return W.swashes_dambreak_2d(n=n, dtype=dtype)
     if kind == "terrain":
-        return W.terrain_case(n=n, dtype=dtype, level=1.0)
+        return W.terrain_case(n=n, dtype=dtype, level=1.0, bc=BC)
     if kind == "urban":
-        return W.urban_case(n=n, dtype=dtype, level=1.0)
-    return W.lake_case(n=n, ny=ny, dtype=dtype, level=LAKE_LEVEL)
+        return W.urban_case(n=n, dtype=dtype, level=1.0, bc=BC)
+    case, state = W.lake_case(n=n, ny=ny, dtype=dtype, level=LAKE_LEVEL)
+    case["bc"] = BC
+    return case, state
 
 
+BC = "wall"          # --bc: "neumann" = the BC of the reference's own terrain / urban examples (examples/terrain.jl:85)
 LAKE_LEVEL = 0.0     # --level: still-water level of the config-5 lake (0 = the bench line, 54 % wet; 60 = every cell wet)
 
 
@@ -234,7 +237,8 @@ def run_reference(args, rank):
 
 def workload_config(args, n, wet):
     if args.config != 5:
-        return {"workload": f"{CONFIGS[args.config][5]}; {n}x{n} {args.dtype}, {wet:.0%} of cells wet",
+        return {"workload": f"{CONFIGS[args.config][5].replace('WallBC', BC + ' BC') if BC != 'wall' else CONFIGS[args.config][5]}"
+                            f"{'' if BC == 'wall' or 'BC' in CONFIGS[args.config][5] else ', ' + BC + ' BC'}; {n}x{n} {args.dtype}, {wet:.0%} of cells wet",
                 "grid": [n, n], "arithmetic": "fast" if not args.strict else "strict", "parallelism": "single GPU",
                 "l2": "3 volumes of %.0f MB" % (3 * 3 * (n + 4) ** 2 * np.dtype(args.dtype).itemsize / 1e6)
                       + (" fit the 126 MB L2: an L2 flush (256 MB memset) runs between timed steps" if args.flush_l2 else "")}
@@ -408,15 +412,15 @@ def run_ours(args, rank, world):
     peak, peak_src = hbm_peak()
     W1, W2 = CONFIGS[args.config][3], CONFIGS[args.config][4]
     ns2 = max(tm["stage_launches"] // 2, 1)
-    k2_ms = tm["stage2_ms"] / ns2
-    k1_ms = tm["stage1_ms"] / ns2
+    k2_ms = tm["stage2_ms"] / ns2 or float("nan")      # (per-operator path: no fused stage kernels to time)
+    k1_ms = tm["stage1_ms"] / ns2 or float("nan")
     achieved = W2 * itemsize * cells_local / (k2_ms * 1e-3) / 1e9
     # dram__bytes_read + write of ONE K2 launch from an `ncu --set full` capture of exactly this launch shape
     # (profiles/traffic.json, keyed by dtype, grid and config); null when no capture exists for it (N > 1 strips, --ny,
     # --level, other sizes): a number measured on another launch would not describe this one
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
-    if tf.exists() and world == 1 and not args.ny and LAKE_LEVEL == 0.0 and not args.strict and not args.unfused:
+    if tf.exists() and world == 1 and not args.ny and LAKE_LEVEL == 0.0 and BC == "wall" and not args.strict and not args.unfused:
         try:
             traffic = json.loads(tf.read_text()).get(f"k_stage2_{args.dtype}_{n}" + ("" if args.config == 5 else f"_config{args.config}"))
         except Exception:
@@ -497,14 +501,17 @@ def main():
                     help="N > 1: equal-height y-strips instead of the cost-balanced partition")
     ap.add_argument("--level", type=float, default=0.0,
                     help="config 5: still-water level of the lake (0 = the bench line, ~54 %% of the cells wet; 60 floods every cell)")
+    ap.add_argument("--bc", default="wall", choices=["wall", "periodic", "neumann"],
+                    help="boundary condition of the workload (N = 1; the bench line uses WallBC)")
     ap.add_argument("--dry-cost", type=float, default=0.6, dest="dry_cost",
                     help="cost of a dry cell relative to a wet one in the strip balancing model")
     args = ap.parse_args()
     args.n = args.n or CONFIGS[args.config][1]
     args.dtype = args.dtype or CONFIGS[args.config][2]
     args.flush_l2 = 3 * 3 * (args.n + 4) * ((args.ny or args.n) + 4) * np.dtype(args.dtype).itemsize < 4 * 126e6
-    global LAKE_LEVEL
+    global LAKE_LEVEL, BC
     LAKE_LEVEL = args.level
+    BC = args.bc
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -1,0 +1,29 @@
+#!/bin/bash
+# round 2: NeumannBC on the packed kernels (tests + timings), K1 at 3 vs 4 resident blocks (interleaved A/B)
+mkdir -p gpurun_out
+V=$PWD/scratch/variants
+( timeout 900 python -m pytest tests/test_gpu_parity_r2.py tests/test_gpu_randomized.py -m gpu -q --maxfail=12 2>&1 | tail -40 ) > gpurun_out/r02h_pytest.txt
+tail -6 gpurun_out/r02h_pytest.txt
+run() { echo -n "$1 :: $2 : "; env $1 python bench.py --no-cpu --steps 20 --warmup 5 $2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print('%s ms/step %.4f  K1 %.4f  K2 %.4f  K2-frac %.3f step-frac %.3f launches %d clocks %s %s' % (r['kernel_family'], d['ms_per_step'], r['k1']['avg_launch_ms'], r['avg_launch_ms'], r['frac'], r['step']['frac'], d['gpu_launches'], d['clocks']['sm_mhz'], d['clocks']['reasons']))"; }
+{
+for i in 1 2 3; do
+run "A=1" ""
+run "SWE_B200_LIB=$V/libswe_b200_k1m3.so" ""
+done
+run "A=1" "--steps 40"
+run "SWE_B200_LIB=$V/libswe_b200_k1m3.so" "--steps 40"
+run "A=1" "--config 3"
+run "SWE_B200_LIB=$V/libswe_b200_k1m3.so" "--config 3"
+run "A=1" "--config 4"
+run "SWE_B200_LIB=$V/libswe_b200_k1m3.so" "--config 4"
+run "A=1" "--ny 2048"
+run "SWE_B200_LIB=$V/libswe_b200_k1m3.so" "--ny 2048"
+run "A=1" "--config 3 --bc neumann"
+run "A=1" "--config 3 --bc neumann --unfused"
+run "A=1" "--config 4 --bc neumann"
+run "A=1" "--config 4 --bc neumann --unfused"
+} > gpurun_out/r02h_ab.txt 2>&1
+cat gpurun_out/r02h_ab.txt

@@ -42,7 +42,9 @@ def test_kernel_family_report(P):
     assert fam(pure) == "per-operator"
     urban, _ = cases.urban_case(n=64, dtype="float32", level=1.0, wavelength=32.0)
     assert fam(urban) == "fused-x2"
-    assert fam(dict(urban, bc="neumann")) in ("fused-x2", "fused-generic", "per-operator")
+    assert fam(dict(urban, bc="neumann")) == "fused-x2"             # NeumannBC (examples/urban.jl:125) on the packed kernels
+    assert fam(dict(lake64, bc="neumann")) in ("fused-d1", "fused-generic")
+    assert fam(dict(urban, bc="neumann"), fused=False) == "per-operator"
 
 
 def test_compare_states_matches_numpy(P):
@@ -234,6 +236,95 @@ def test_swashes_422b_planar_surface_in_paraboloid(P, dtype):
     # wall BC: mass is conserved up to round-off and the dry clean-up's w = max(w, B_cell) (timestepper.jl:41-51), which
     # creates water in cells that dip below the bed: 3e-4 relative in Float32 over the ~64 000 steps of one rotation
     assert s.diagnostics()["sum_h"] == pytest.approx(v0, rel=1e-10 if dtype == "float64" else 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# NeumannBC on the fused path (bc.jl:49-60; the BC of examples/terrain.jl:85 and examples/urban.jl:125)
+# ------------------------------------------------------------------------------------------------------------------
+NEUMANN_CASES = {
+    "terrain_rk2": lambda dt: cases.terrain_case(n=96, dtype=dt, bc="neumann", level=0.0, wavelength=64.0, friction="bh2021"),
+    "terrain_fe_dry": lambda dt: cases.terrain_case(n=72, dtype=dt, bc="neumann", wavelength=48.0, stepper="fe", film=0.12),
+    "urban_norecon": lambda dt: cases.urban_case(n=80, dtype=dt, bc="neumann", level=0.5, wavelength=64.0),
+    "lake_bh2021": lambda dt: dict(cases.lake_case(n=100, ny=77, dtype=dt, wavelength=48.0)[0], bc="neumann"),
+}
+
+
+def _neumann(name, dtype):
+    got = NEUMANN_CASES[name](dtype)
+    if isinstance(got, dict):
+        return got, cases.lake_case(n=100, ny=77, dtype=dtype, wavelength=48.0)[1]
+    return got
+
+
+def _no_corners(a, gc=2):
+    m = np.ones(a.shape[1:], dtype=bool)
+    m[:gc, :gc] = m[:gc, -gc:] = m[-gc:, :gc] = m[-gc:, -gc:] = False
+    return a[:, m]
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", sorted(NEUMANN_CASES))
+def test_neumann_fused_strict_bit_exact(P, oracle, name, dtype):
+    """interior AND ghost cells (the self-evolving high-side ghosts included), every step's dt, fused == per-operator"""
+    case, state = _neumann(name, dtype)
+    mts = case.get("maximum_timestep", math.inf)
+    s = P.simulator_from_case(case, strict=True, fused=True)
+    u = P.simulator_from_case(case, strict=True, fused=False)
+    o = oracle.OracleSim(case)
+    assert s.kernel_family() == "fused-generic" and u.kernel_family() == "per-operator"
+    for x in (s, u, o):
+        x.set_state_interior(*state)
+    cbrt = case.get("friction") in ("bsa2012", "fcg2016")
+    for n in range(25):
+        for x in (s, u, o):
+            x.step(mts)
+        if cbrt:
+            assert s.dt == pytest.approx(o.dt, rel=1e-12)
+        else:
+            assert s.dt == o.dt == u.dt, f"step {n}: dt {s.dt} vs {o.dt}"
+    a, b, c = (_no_corners(x.get_state_full()) for x in (s, o, u))
+    if cbrt:
+        assert max(cases.field_errors(a, b)) <= (1e-12 if dtype == "float64" else 1e-5)
+    else:
+        assert np.array_equal(a, b), f"max diff {np.max(np.abs(a - b))}"
+        assert np.array_equal(a, c)
+    assert np.any(s.get_state_full()[:, 2:-2, -1] != 0)            # the outermost high ghost column holds evolved data
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", F64_TOL), ("float32", F32_TOL)])
+@pytest.mark.parametrize("name", ["terrain_rk2", "lake_bh2021"])
+def test_neumann_fused_fast_within_tolerance(P, oracle, name, dtype, tol):
+    """fast policies under NeumannBC (x2 / d1 kernels).  The image of the top rows in the low-y ghosts and the
+    self-evolving high-side ghosts put discontinuities on the boundary, so the lake case is ill-conditioned from the
+    first steps (the oracle's own +-1 ulp sensitivity after 20 steps is 9e-5 in Float32; 3e-7 under WallBC): the bound is
+    max(tolerance, 4 x that sensitivity) like in test_gpu_parity.py."""
+    case, state = _neumann(name, dtype)
+    mts = case.get("maximum_timestep", math.inf)
+
+    def run_oracle(st):
+        o = oracle.OracleSim(case)
+        o.set_state_interior(*st)
+        for _ in range(20):
+            o.step(mts)
+        return o.get_state_full()[:, 2:-2, 2:-2], o.t
+
+    b, t_ref = run_oracle(state)
+    sens = np.max([cases.field_errors(run_oracle(cases.perturb_ulp(state, dtype, seed=sd))[0], b) for sd in (1, 2, 3)], axis=0)
+    s = P.simulator_from_case(case)
+    s.set_state_interior(*state)
+    for _ in range(20):
+        s.step(mts)
+    assert s.kernel_family() == ("fused-d1" if dtype == "float64" else "fused-x2")
+    err = cases.field_errors(s.get_state_full()[:, 2:-2, 2:-2], b)
+    for e, sn in zip(err, sens):
+        assert e <= max(tol, 4 * sn), (err, list(sens))
+    assert s.t == pytest.approx(t_ref, rel=max(10 * tol, 1e-6))
+
+
+def test_neumann_multi_strip_is_refused(P):
+    case, state = _neumann("lake_bh2021", "float32")
+    with pytest.raises(P.B200Error):
+        P.multigpu.LocalStripGroup(case, state, [0, 0])
 
 
 # ------------------------------------------------------------------------------------------------------------------

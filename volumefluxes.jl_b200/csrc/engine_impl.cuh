@@ -176,11 +176,13 @@ public:
         for (int q = 0; q < 16; ++q) { rt.rates[q] = c.rain_rates[q]; rt.times[q] = c.rain_times[q]; }
         ip.kind = c.infil_kind; ip.cst = c.infil_const; ip.f0 = c.f0; ip.fc = c.fc; ip.k = c.k;
         // the fused stage kernels cover the practical 2D SWE with gc == 2 and periodic / wall BCs
-        fused_ok = c.fused && c.eq_kind == 0 && gc == 2 && c.bc != SWE_B200_BC_NEUMANN && c.nx >= 4 && c.ny >= 4;
+        // (NeumannBC: single strip only -- its low-y ghosts are images of the TOP interior rows and its high-y ghosts evolve
+        // on their own, kernels_fused.cuh k_neumann_*; a y-strip version would need a one-directional wrap-around exchange)
+        fused_ok = c.fused && c.eq_kind == 0 && gc == 2 && c.nx >= 4 && c.ny >= 4 && !(c.bc == SWE_B200_BC_NEUMANN && multi);
         setup_x2(c);
         setup_d1(c);
         if (multi && !fused_ok) {
-            err = "y-strip decomposition needs the fused path (ShallowWaterEquations, gc == 2, periodic/wall BC)";
+            err = "y-strip decomposition needs the fused path (ShallowWaterEquations, gc == 2, periodic / wall BC)";
             return SWE_B200_EUNSUPPORTED;
         }
         SWE_CUDA(cudaStreamSynchronize(stream));
@@ -833,6 +835,12 @@ public:
             k_ctl_dt<S><<<1, 1, 0, stream>>>(ctl, par_dx(), par_dy(), (S)cfg.cfl);
             ++launches;
         }
+        const bool neumann = cfg.bc == SWE_B200_BC_NEUMANN;
+        const int nline = (int)((Ny + Nx - 1 + 127) / 128);
+        if (neumann) {       // dU of the self-evolving outermost high ghost column / row = the per-cell sources
+            k_neumann_dU<P><<<nline, 128, 0, stream>>>(par, D, ctl, factor, rainp, cfg.rain_kind, cfg.infil_kind, cfg.infil_first);
+            ++launches;
+        }
         mark("dt(+push dU)");
         S* next;
         int next_index;
@@ -841,12 +849,14 @@ public:
             next_index = cur[2];
             launch_stage<2>(U, D, next);
             mark("K2");
+            if (neumann) { k_neumann_ghosts<P, true><<<nline, 128, 0, stream>>>(par, bathy(), U, D, next, ctl); ++launches; }
             std::swap(cur[0], cur[2]);
         } else {
             dim3 b(32, 8), g((cfg.nx + 31) / 32, (cfg.ny + 7) / 8);
             if (B) k_update_fe<P, true><<<g, b, 0, stream>>>(par, bathy(), U, D, ctl);
             else k_update_fe<P, false><<<g, b, 0, stream>>>(par, bathy(), U, D, ctl);
             ++launches;
+            if (neumann) { k_neumann_ghosts<P, false><<<nline, 128, 0, stream>>>(par, bathy(), U, D, D, ctl); ++launches; }
             next = D;
             next_index = cur[1];
             std::swap(cur[0], cur[1]);

@@ -212,7 +212,7 @@ __device__ __forceinline__ void bc_fill(S* d, int Nx, int Ny, long long plane, i
     const bool flip = bc == SWE_B200_BC_WALL && k == normal;
     const int a = side == 0 ? g : N - 1 - g;
     bool f;
-    const S v = base[(size_t)bc_source(a, N, gc, bc, true, true, f) * sa];
+    const S v = base[(size_t)bc_source(a, N, gc, bc, true, true, f, dir) * sa];
     base[(size_t)a * sa] = flip ? -v : v;          // a copy or a sign flip: exact for subnormals too
 }
 template <class S>

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
             u[2] = s[2 * plane];
         } else {
             bool yflip;
-            const int ys = bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
+            const int ys = bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip, 1);
             const size_t off = (size_t)ys * Nx + xs;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
             for (int k = 0; k < 3; ++k) q[k] = u[k];
         } else {
             bool yflip;
-            const int ys = bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
+            const int ys = bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip, 1);
 #pragma unroll
             for (int k = 0; k < 3; ++k) un[k] = u[k];
             C Bm = bc_actual;
@@ -324,6 +324,91 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
             if (by) atomicMax(&a.ctl->maxspeed_bits[1], by);
         }
     }
+}
+
+// ---- NeumannBC on the fused path (bc.jl:49-60) ----------------------------------------------------------------------
+// The low-side ghosts are copies of interior cells (X: mirror, Y: image of the top interior rows) and are rebuilt /
+// filled like the other BCs.  The high-side ghosts are not: the reference's ghost<->ghost copy (bc.jl:52-53, 57-58)
+// leaves both layers holding the OLD outermost ghost cell, which therefore evolves on its own through the operators the
+// reference applies to ALL cells -- sources (source_term_rain.jl:71-76, source_term_infiltration.jl:83-88), the stage
+// update (rungekutta.jl:39-49), implicit friction (friction.jl:80-84), dry clean-up (timestepper.jl:41-51) -- with no
+// flux and no bottom source (interior only).  Two small kernels per step carry that evolution:
+//   k_neumann_dU     (before stage 2): dU := the per-cell sources on the outermost high ghost column / row, so that
+//                    stage 2's on-the-fly rebuild U^1 = tail(U^n + dt dU) is right for the ghost source cells;
+//   k_neumann_ghosts (before the tail): U^{n+1} of those cells (both RK2 stages, or the one ForwardEuler stage); the
+//                    tail's ghost fill then copies them into the inner ghost layer.
+template <class P>
+__device__ __forceinline__ void neumann_line_cell(long long t, int Nx, int Ny, int& i, int& j) {
+    // t in [0, Ny): column Nx-1, row t ; t in [Ny, Ny + Nx - 1): row Ny-1, column t - Ny
+    if (t < Ny) { i = Nx - 1; j = (int)t; }
+    else { i = (int)(t - Ny); j = Ny - 1; }
+}
+template <class P>
+__global__ void k_neumann_dU(Par<typename P::C> p, typename P::S* D, const Ctl* ctl, const double* factor, const double* rainp,
+                             int rain_kind, int infil_kind, int infil_first) {
+    using S = typename P::S;
+    using C = typename P::C;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)p.Ny + p.Nx - 1) return;
+    int i, j;
+    neumann_line_cell<P>(t, p.Nx, p.Ny, i, j);
+    const size_t q = (size_t)j * p.Nx + i;
+    S d0 = 0;                                             // rungekutta.jl:28-30: out = 0, then the source terms in list order
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool do_infil = (pass == 0) == (infil_first != 0);
+        if (do_infil && infil_kind != SWE_B200_INFIL_NONE) {
+            const C f = factor ? (C)(factor[q] * ctl->infil) : (C)ctl->infil;
+            d0 = (S)(d0 - f);
+        }
+        if (!do_infil && rain_kind != SWE_B200_RAIN_NONE) d0 = (S)(d0 + (rainp ? (C)rainp[q] : (C)ctl->rain));
+    }
+    D[q] = d0;
+    D[q + p.plane] = 0;
+    D[q + 2 * p.plane] = 0;
+}
+template <class P, bool RK2>
+__global__ void k_neumann_ghosts(Par<typename P::C> p, Bathy<P> bt, const typename P::S* U, const typename P::S* D,
+                                 typename P::S* out, const Ctl* ctl) {
+    using S = typename P::S;
+    using C = typename P::C;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)p.Ny + p.Nx - 1) return;
+    int i, j;
+    neumann_line_cell<P>(t, p.Nx, p.Ny, i, j);
+    const size_t q = (size_t)j * p.Nx + i;
+    S st[3], d[3], u1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { st[k] = U[q + k * p.plane]; d[k] = D[q + k * p.plane]; }
+    const C dt = (C)ctl->dt;
+    const S dt_s = (S)ctl->dt_s;
+    const C Bm = bt.cell(i, j);
+    substep_tail<P>(p, st, d, dt, dt_s, Bm, u1);         // stage 1 (or the ForwardEuler step)
+    if (!RK2) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out[q + k * p.plane] = u1[k];
+        return;
+    }
+    S o[3];                                               // stage 2 exactly as k_stage<.., STAGE = 2> finishes a cell
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o[k] = (S)(u1[k] + dt_s * d[k]);
+        o[k] = (S)((C)0.5 * (S)(st[k] + o[k]));
+    }
+    if (p.friction != SWE_B200_FRICTION_NONE) {
+        const C den = friction_denominator<P, false>(p, u1[0], u1[1], u1[2], Bm, dt_s);
+        if constexpr (P::strict) {
+            o[1] = (S)(o[1] / den);
+            o[2] = (S)(o[2] / den);
+        } else {
+            const C rden = rcp_fast(den);
+            o[1] = (S)(o[1] * rden);
+            o[2] = (S)(o[2] * rden);
+        }
+    }
+    post_proc_cell<P>(p, o, Bm);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[q + k * p.plane] = o[k];
 }
 
 // ForwardEuler tail, in place: vol = postproc(friction(U^n + dt*dU)) on the interior

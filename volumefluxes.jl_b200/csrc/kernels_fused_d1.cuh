@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_d1(const Args1 a) {
     auto row_source = [&](int j, bool& yflip) -> int {   // stage 2: the row the y BC copies row j from
         yflip = false;
         if (STAGE == 1) return j;
-        return bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
+        return bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip, 1);
     };
     // stage 1: q = U^n ; stage 2: q = U^1 = BC(postproc(friction(U^n + dt*dU))) rebuilt on the fly
     auto finish_row = [&](bool remapped, int ys, bool yflip, const R u[3], const R d[3], R Bc_here, R q[3]) {

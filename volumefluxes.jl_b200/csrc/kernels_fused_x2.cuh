@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int Nx = p.Nx, Ny = p.Ny;
-    f2 msx = sp(0.0f), msy = sp(0.0f);                   // running CFL maxima of this thread (stage 1)
+    f2 msx = sp(0.0f);                                   // running CFL maxima of this thread (stage 1): x faces a / b,
+    float msy = 0.0f;                                    // y faces of both columns (same predicate: one FMNMX3 per row)
     // Work queue: every WARP is independent (its own ring columns, no barrier), so warps pull (tile, rows)
     // items from one atomic counter until the grid is done.  The item table is a guided schedule (EngineT::
     // build_items): 126-row items first, then 63-, 30- and 12-row items, so that all 148 SMs stay busy to the
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
     f2 dt = sp(0.0f), czdt = sp(0.0f);
     int xs = ic;
     bool xswap = false;
+    int xmode = 0;                                       // ghost pair: 0 mirrored + normal momentum flipped (wall), 1 mirrored (Neumann low), 2 outermost ghost twice (Neumann high)
     if (STAGE == 2) {
         const float dts = (float)a.ctl->dt_s;
         dt = sp(dts);
@@ -416,7 +418,11 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
         if (ic < 2 || ic >= Nx - 2) {                    // a pair of x ghosts: where the BC copies them from
             const bool lo = ic < 2;
             if (p.bc == SWE_B200_BC_PERIODIC) xs = lo ? Nx - 4 : 2;
-            else { xs = lo ? 2 : Nx - 4; xswap = true; }   // wall: mirrored pair, normal momentum flips
+            else if (p.bc == SWE_B200_BC_NEUMANN) {        // bc.jl:51-53: low = mirrored pair (no sign flip); high = both
+                xswap = true;                              // ghosts hold the self-evolving outermost ghost column
+                xmode = lo ? 1 : 2;                        // (k_neumann_dU / k_neumann_ghosts): its own pair, .y twice
+                if (lo) xs = 2;
+            } else { xs = lo ? 2 : Nx - 4; xswap = true; }   // wall: mirrored pair, normal momentum flips
         }
     }
     // per-cell sources (system.jl:71-73): rain - infiltration is one constant per step unless a Horton factor plane exists
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
     auto row_source = [&](int j, bool& yflip) -> int {   // stage 2: the row the y BC copies row j from
         yflip = false;
         if (STAGE == 1) return j;
-        return bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip);
+        return bc_source(j, Ny, 2, p.bc, p.ylo_phys, p.yhi_phys, yflip, 1);
     };
     // stage 1: q = U^n ; stage 2: q = U^1 = BC(postproc(friction(U^n + dt*dU))) rebuilt on the fly
     const bool xghost = xs != ic;
@@ -457,8 +463,8 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
             q[2] = mul(q[2], fac);
             if (!FASTROW && ghost_warp && xswap) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) q[k] = swp(q[k]);
-                q[1] = neg(q[1]);
+                for (int k = 0; k < 3; ++k) q[k] = xmode == 2 ? sp(q[k].y) : swp(q[k]);
+                if (xmode == 0) q[1] = neg(q[1]);
             }
             if (!FASTROW && yflip) q[2] = neg(q[2]);
         }
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
         f2 s = sp(0.0f);
         Gl[0] = Gl[1] = Gl[2] = sp(0.0f);
         if (__any_sync(0xffffffffu, any_wet(p, Rp[0], Ly0[0]))) cu2<1, STAGE == 1>(p, Rp, Ly0, Gl, s);   // face ja-1/2
-        if (STAGE == 1 && out_pair) { msy.x = fmaxf(msy.x, s.x); msy.y = fmaxf(msy.y, s.y); }
+        if (STAGE == 1 && out_pair) msy = fmaxf(msy, fmaxf(s.x, s.y));
         hsy = add(Ly0[0], Ry0[0]);
         Ej = c[2];
         tyj = t0;
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
                 if (STAGE == 1 && (FAST || j < jb)) {
                     if (facea_ok) msx.x = fmaxf(msx.x, sx.x);
                     if (faceb_ok) msx.y = fmaxf(msx.y, sx.y);
-                    if (out_pair) { msy.x = fmaxf(msy.x, sy.x); msy.y = fmaxf(msy.y, sy.y); }
+                    if (out_pair) msy = fmaxf(msy, fmaxf(sy.x, sy.y));
                 }
             } else {
 #pragma unroll
@@ -760,7 +766,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
 
     if (STAGE == 1) {
         // CFL reduction: warp shuffle -> one atomicMax per warp and direction (non-negative bit patterns)
-        unsigned bx = __float_as_uint(fmaxf(msx.x, msx.y)), by = __float_as_uint(fmaxf(msy.x, msy.y));
+        unsigned bx = __float_as_uint(fmaxf(msx.x, msx.y)), by = __float_as_uint(msy);
         bx = __reduce_max_sync(0xffffffffu, bx);
         by = __reduce_max_sync(0xffffffffu, by);
         if (lane == 0) {

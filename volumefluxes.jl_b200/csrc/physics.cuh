@@ -352,17 +352,22 @@ __device__ __forceinline__ void post_proc_cell(const Par<typename P::C>& p, type
 // ---- ghost-cell source map (bc.jl:29-40 periodic, :81-110 wall).  0-based index a in [0,N),
 // returns the 0-based index whose value the BC copies into a (a itself if not a physical ghost)
 // and whether the normal momentum changes sign. ------------------------------------------------------
-__device__ __forceinline__ int bc_source(int a, int N, int gc, int bc, bool lo_phys, bool hi_phys, bool& flip) {
+__device__ __forceinline__ int bc_source(int a, int N, int gc, int bc, bool lo_phys, bool hi_phys, bool& flip, int dir = 0) {
     flip = false;
     if (a < gc) {
         if (!lo_phys) return a;
         if (bc == SWE_B200_BC_PERIODIC) return a + N - 2 * gc;
-        flip = (bc == SWE_B200_BC_WALL);
+        if (bc == SWE_B200_BC_NEUMANN) return dir == 0 ? 2 * gc - 1 - a : a + N - 2 * gc;   // bc.jl:51,56 (X: mirror, Y: the
+        flip = (bc == SWE_B200_BC_WALL);                                                     // image of the top interior rows)
         return 2 * gc - 1 - a;
     }
     if (a >= N - gc) {
         if (!hi_phys) return a;
         if (bc == SWE_B200_BC_PERIODIC) return a - N + 2 * gc;
+        // NeumannBC high side (bc.jl:52-53, 57-58): ghost g=1 copies the outermost ghost, then g=2 copies g=1 back --
+        // both end up holding the OLD outermost ghost cell, which never sees interior data and evolves on its own
+        // (sources, friction, dry clean-up act on all cells): see k_neumann_dU / k_neumann_ghosts
+        if (bc == SWE_B200_BC_NEUMANN) return N - 1;
         flip = (bc == SWE_B200_BC_WALL);
         return 2 * (N - gc) - 1 - a;
     }
