@@ -309,7 +309,8 @@ def test_neumann_fused_fast_within_tolerance(P, oracle, name, dtype, tol):
         return o.get_state_full()[:, 2:-2, 2:-2], o.t
 
     b, t_ref = run_oracle(state)
-    sens = np.max([cases.field_errors(run_oracle(cases.perturb_ulp(state, dtype, seed=sd))[0], b) for sd in (1, 2, 3)], axis=0)
+    # four seeds: the sensitivity is heavy-tailed (one dry-state switch flips or it does not: seeds 1-3 give 1e-5, seed 4 9e-5)
+    sens = np.max([cases.field_errors(run_oracle(cases.perturb_ulp(state, dtype, seed=sd))[0], b) for sd in (1, 2, 3, 4)], axis=0)
     s = P.simulator_from_case(case)
     s.set_state_interior(*state)
     for _ in range(20):

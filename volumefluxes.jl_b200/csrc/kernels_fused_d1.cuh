@@ -43,6 +43,12 @@ constexpr int minb() { return STAGE == 2 ? D1_MINB2 : D1_MINB; }
 
 __device__ __forceinline__ R vmin(R a, R b) { return a < b ? a : b; }
 __device__ __forceinline__ R vmax(R a, R b) { return a > b ? a : b; }
+// The kernel is bound by the FP64 pipe (profiles/r02f_ncu_d1_f64_4096.txt: 62 % busy, the top pipe; DSETP runs there
+// too).  Comparisons whose operands are known to be non-negative, and tests against zero, are done on the bit patterns
+// by the integer ALU instead -- the ordering of non-negative doubles is the ordering of their bit patterns.
+__device__ __forceinline__ R vmin_nn(R a, R b) { return __double_as_longlong(a) < __double_as_longlong(b) ? a : b; }
+__device__ __forceinline__ R vmax_nn(R a, R b) { return __double_as_longlong(a) > __double_as_longlong(b) ? a : b; }
+__device__ __forceinline__ R relu(R x) { return __double2hiint(x) < 0 ? 0.0 : x; }
 __device__ __forceinline__ R rcp_n(R x) {                // hardware seed (~2^-20) + two Newton steps: ~1 ulp
     R r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -57,7 +63,7 @@ __device__ __forceinline__ R sqrt_n(R x) {               // x >= 0: rsqrt seed (
     y = y * fma(-0.5 * x * y, y, 1.5);
     R s = x * y;
     s = fma(fma(-s, s, x), 0.5 * y, s);
-    return x > 1e-300 ? s : 0.0;                         // (rsqrt(0) = inf; the flush-to-zero seed does not see subnormals)
+    return __double2hiint(x) >= 0x00100000 ? s : 0.0;    // normal x only (rsqrt(0) = inf; the flush-to-zero seed does not see subnormals)
 }
 __device__ __forceinline__ R shfl_up(R v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ R shfl_dn(R v) { return __shfl_down_sync(0xffffffffu, v, 1); }
@@ -88,10 +94,10 @@ struct Args1 {
 // ---- minmod-limited slope from the backward / forward differences (linearreconstruction.jl:28-43) ----------------
 __device__ __forceinline__ R slope(R theta, R b, R f) {
     const R af = fabs(f), ab = fabs(b);
-    const R m1 = vmin(af, ab);
-    const R m2 = vmin(theta * m1, 0.5 * (af + ab));
+    const R m1 = vmin_nn(af, ab);
+    const R m2 = vmin_nn(theta * m1, 0.5 * (af + ab));
     // equal strict signs, tested on the sign bits (a product f * b would underflow for tiny differences)
-    const bool same = ((__double2hiint(f) ^ __double2hiint(b)) >= 0) && m1 > 0.0;
+    const bool same = ((__double2hiint(f) ^ __double2hiint(b)) >= 0) && __double_as_longlong(m1) != 0ll;
     return same ? copysign(m2, f) : 0.0;
 }
 
@@ -124,7 +130,7 @@ __device__ __forceinline__ void recon1(const Par1& p, const R c[3], const R bwd[
 
 // desingularised depth of a NON-NEGATIVE depth (equation.jl:56-62): max(h, min(h^2/2k + k/2, k)) = h + relu(k - h)^2 / 2k
 __device__ __forceinline__ R desing_pos(const Par1& p, R h) {
-    const R rl = vmax(p.kappa - h, 0.0);
+    const R rl = relu(p.kappa - h);
     return fma(rl * rl, p.i2k, h);
 }
 
@@ -132,11 +138,11 @@ __device__ __forceinline__ R desing_pos(const Par1& p, R h) {
 // (swe_2D.jl:43-81, equation.jl:40-62, centralupwind.jl:54-63) ----------------------------------------------------
 template <int DIR>
 __device__ __forceinline__ void side1(const Par1& p, R h, R hu, R hv, R F[3], R& ep, R& en) {
-    const R m = h > p.cutoff ? 1.0 : 0.0;
-    const R hm = h * m;
+    const bool wet = h > p.cutoff;
+    const R hm = wet ? h : 0.0;
     const R pres = p.K * (hm * hm);
     const R c = sqrt_n(p.g * hm);
-    const R rm = rcp_n(desing_pos(p, hm)) * m;
+    const R rm = rcp_n(desing_pos(p, hm)) * (wet ? 1.0 : 0.0);     // (a multiply, not a select: no branch around the Newton steps)
     const R u = hu * rm, v = hv * rm;
     const R rh = p.rho * hm;
     R un;
@@ -161,8 +167,8 @@ __device__ __forceinline__ void cu1(const Par1& p, const R Um[3], const R Up[3],
     R Fm[3], Fp[3], epm, enm, epp, enp;
     side1<DIR>(p, Um[0], Um[1], Um[2], Fm, epm, enm);
     side1<DIR>(p, Up[0], Up[1], Up[2], Fp, epp, enp);
-    const R ap = vmax(vmax(epm, epp), 0.0);              //  a+
-    const R an = vmax(vmax(enm, enp), 0.0);              // -a-
+    const R ap = relu(vmax(epm, epp));                   //  a+
+    const R an = relu(vmax(enm, enp));                   // -a-
     const R d = ap + an;
     const bool ok = !(d < p.kappa);                      // :67-69
     const R r = ok ? rcp_n(d) : 0.0;
@@ -170,7 +176,7 @@ __device__ __forceinline__ void cu1(const Par1& p, const R Um[3], const R Up[3],
     const R c2 = ap * wn;
 #pragma unroll
     for (int k = 0; k < 3; ++k) F[k] = fma(c2, Um[k] - Up[k], fma(wn, Fp[k], wp * Fm[k]));
-    speed = (SPEED && ok) ? vmax(ap, an) : 0.0;
+    speed = (SPEED && ok) ? vmax_nn(ap, an) : 0.0;
 }
 
 // ---- pointwise tail of a substep (rungekutta.jl:39-41, friction.jl:62-84, timestepper.jl:41-51): returns the factor
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_d1(const Args1 a) {
         R s = 0.0;
         Gl[0] = Gl[1] = Gl[2] = 0.0;
         if (__any_sync(0xffffffffu, vmax(Rp[0], Ly0[0]) > p.cutoff)) cu1<1, STAGE == 1>(p, Rp, Ly0, Gl, s);   // face ja-1/2
-        if (STAGE == 1 && out_lane) msy = vmax(msy, s);
+        if (STAGE == 1 && out_lane) msy = vmax_nn(msy, s);
         hsy = Ly0[0] + Ry0[0];
         Ej = c[2];
         tyj = t0;
@@ -468,8 +474,8 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_d1(const Args1 a) {
                 cu1<0, STAGE == 1>(p, Rx, Ln, F, sx);
                 cu1<1, STAGE == 1>(p, Ry0, Ly1, G, sy);
                 if (STAGE == 1 && (FAST || j < jb)) {
-                    if (xface_ok) msx = vmax(msx, sx);
-                    if (out_lane) msy = vmax(msy, sy);
+                    if (xface_ok) msx = vmax_nn(msx, sx);
+                    if (out_lane) msy = vmax_nn(msy, sy);
                 }
             } else {
 #pragma unroll
