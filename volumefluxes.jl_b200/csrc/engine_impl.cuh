@@ -302,6 +302,21 @@ public:
         const long long L = (long long)ntiles * c.ny;
         // small grids: a big item is at most about half of a warp's whole share of tile-rows
         if (!std::getenv("SWE_B200_X2_ROWS")) big = (int)std::min<long long>(big, std::max<long long>(12, L / W / 2 / 3 * 3));
+        // tiny grids (a warp's whole share is below 36 tile-rows, e.g. 1024^2: 16): the guided classes degenerate into
+        // 12-row items, 1.3 per resident warp.  SWE_B200_X2_ONEWAVE=1 selects ONE wave of equal items instead, one per
+        // resident warp (ceil(share) rows + one prologue).  Measured (profiles/r02j_ab_onewave.txt): no gain -- 1024^2
+        // Float64 0.102 vs 0.098 ms/step, +-2 % on seven other small configurations; a 40 us launch on a grid of this
+        // size is ramp, first-touch DRAM latency and the tail, not the item shape.  Off by default.
+        bool one_wave = false;
+        if (!std::getenv("SWE_B200_X2_ROWS") && L < 36 * W) {
+            const char* e = std::getenv("SWE_B200_X2_ONEWAVE");
+            if (e && e[0] == '1') {
+                // rows per item: the smallest multiple of 3 whose item count (whole items per tile column) fits one wave
+                for (int r = 3; r <= 48; r += 3) {
+                    if ((long long)ntiles * ((c.ny + r - 1) / r) <= W) { big = r; one_wave = true; break; }
+                }
+            }
+        }
         int sizes[4] = {big, std::min(63, std::max(12, big / 2 / 3 * 3)), std::min(30, std::max(12, big / 4 / 3 * 3)), 12};
         long long quota[4];
         double per_warp[4] = {0, 1, 1, 1};          // least items of each small class per resident warp
@@ -323,6 +338,7 @@ public:
             quota[0] = L - quota[1] - quota[2] - quota[3];
         }
         if (const char* e = std::getenv("SWE_B200_X2_FLAT")) { if (e[0] == '1') { quota[1] = quota[2] = quota[3] = 0; quota[0] = L; } }
+        if (one_wave) { quota[1] = quota[2] = quota[3] = 0; quota[0] = L; }
         // rows of every tile column per class, top of the column = smallest items (any order works: the classes
         // are emitted class by class, tile-fastest, so neighbours in x run at about the same time -> L2 reuse)
         std::vector<int4> items;
