@@ -308,6 +308,7 @@ def run_ours(args, rank, world):
                 balance.update(rows_measured=list(new_sizes),
                                stage_ms_before=[round(float(m) / args.rebalance, 4) for m in measured])
                 if list(new_sizes) != list(sizes):
+                    strip.close()               # collective: unmap the peers, barrier, destroy
                     del strip, pinned
                     strip = None
                     offs, sizes = new_offs, new_sizes
@@ -406,6 +407,7 @@ def run_ours(args, rank, world):
     if rank != 0:
         barrier()
         if dist is not None:
+            strip.close()
             dist.destroy_process_group()
         return
 
@@ -474,6 +476,7 @@ def run_ours(args, rank, world):
     print(json.dumps(out), flush=True)
     barrier()
     if dist is not None:
+        strip.close()
         dist.destroy_process_group()
 
 

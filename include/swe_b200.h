@@ -194,6 +194,11 @@ int swe_b200_get_ipc_handle(swe_b200_handle* h, void* blob128);
 /* Map every rank's window (all_blobs: nranks x 128 B, ordered by rank).  Afterwards set_state_interior,
  * step, run_steps and simulate_to_time are COLLECTIVE: every rank must issue the same sequence. */
 int swe_b200_open_peers(swe_b200_handle* h, const void* all_blobs128);
+/* Unmap the peers' windows again (waits for this handle's stream first).  COLLECTIVE tear-down order: every rank calls
+ * close_peers, then a host-side barrier, then destroy -- freeing a window that a peer still has mapped is undefined
+ * behaviour in CUDA IPC.  Afterwards the handle is a single-rank handle without neighbours: only get_* / destroy make
+ * sense on it. */
+int swe_b200_close_peers(swe_b200_handle* h);
 
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* Runs n steps like run_steps and returns the device time (CUDA events on the handle's stream)

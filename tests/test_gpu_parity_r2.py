@@ -348,6 +348,24 @@ def test_neumann_fused_fast_within_tolerance(P, oracle, name, dtype, tol):
     assert s.t == pytest.approx(t_ref, rel=max(10 * tol, 1e-6, 4 * float(np.max(sens))))
 
 
+def test_close_peers_then_destroy(P):
+    """collective tear-down order of a strip group: unmap the peers first (swe_b200_close_peers), then destroy"""
+    case, state = cases.lake_case(n=64, ny=48, dtype="float32", wavelength=32.0)
+    grp = P.multigpu.LocalStripGroup(case, state, [0, 0])
+    grp.run_steps(5)
+    ref = grp.gather_interior()
+    L = P.api._lib.lib()
+    for s in grp.sims:
+        s._check(L.swe_b200_close_peers(s._h))
+        s._check(L.swe_b200_close_peers(s._h))          # idempotent
+    parts = [s.get_state_interior() for s in grp.sims]  # the strips' own data stay readable
+    got = [np.concatenate([p[k] for p in parts], axis=0) for k in range(3)]
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    for s in grp.sims:
+        s.close()
+
+
 def test_neumann_multi_strip_is_refused(P):
     case, state = _neumann("lake_bh2021", "float32")
     with pytest.raises(P.B200Error):

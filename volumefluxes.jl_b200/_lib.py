@@ -79,6 +79,7 @@ SYMBOLS = {
     "swe_b200_enumerate_grid": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _pi64]),
     "swe_b200_get_ipc_handle": (_i, [_vp, _vp]),
     "swe_b200_open_peers": (_i, [_vp, _vp]),
+    "swe_b200_close_peers": (_i, [_vp]),
     "swe_b200_run_steps_timed": (_i, [_vp, _i64, _d, C.POINTER(Timing)]),
     "swe_b200_launch_count": (_i, [_vp, _pi64]),
     "swe_b200_kernel_family": (_i, [_vp]),

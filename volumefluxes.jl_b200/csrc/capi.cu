@@ -107,6 +107,7 @@ int swe_b200_enumerate_grid(int kind, int nx, int ny, int gc, int dir, int ghost
 }
 int swe_b200_get_ipc_handle(swe_b200_handle* h, void* p) { FWD(get_ipc_handle(p)); }
 int swe_b200_open_peers(swe_b200_handle* h, const void* p) { FWD(open_peers(p)); }
+int swe_b200_close_peers(swe_b200_handle* h) { FWD(close_peers()); }
 int swe_b200_kernel_family(swe_b200_handle* h) { H_OR_FAIL(h); return h->e->kernel_family(); }
 int swe_b200_compare_states(swe_b200_handle* h, swe_b200_handle* other, int buffer, const double* thresholds,
                             double out[SWE_B200_COMPARE_SLOTS]) {

@@ -38,6 +38,7 @@ struct Engine {
     virtual int enumerate(int kind, int dir, int ghostcells, int64_t* out, int64_t* count) = 0;
     virtual int get_ipc_handle(void* handle64) = 0;
     virtual int open_peers(const void* all_handles64) = 0;
+    virtual int close_peers() = 0;
     virtual int64_t launch_count() const = 0;
     virtual int kernel_family() const = 0;
     virtual const void* state_ptr(int buffer) const = 0;

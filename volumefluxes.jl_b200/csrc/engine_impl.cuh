@@ -1066,6 +1066,19 @@ public:
         peers_open = true;
         return SWE_B200_OK;
     }
+    int close_peers() override {
+        if (!peers_open) return SWE_B200_OK;
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        int rc = check_timeout();
+        for (int r = 0; r < MAX_RANKS; ++r) {
+            if (peer_ipc[r] && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
+            peer_ipc[r] = false;
+            peer_base[r] = nullptr;
+            peer_mbox[r] = nullptr;
+        }
+        peers_open = false;
+        return rc;
+    }
     int check_timeout() {
         if (!peers_open) return SWE_B200_OK;
         unsigned long long t = 0;

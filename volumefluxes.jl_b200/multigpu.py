@@ -112,6 +112,7 @@ class StripSimulator:
     def __init__(self, sub_case: dict, sub_state, rank: int, nranks: int, global_ny: int, y_offset: int,
                  all_gather: Callable[[bytes], List[bytes]], device: int = 0, strict: bool = False):
         self.rank, self.nranks = rank, nranks
+        self._all_gather = all_gather
         self.y0, self.ny, self.global_ny = y_offset, sub_case["ny"], global_ny
         self.sim = api.simulator_from_case(sub_case, strict=strict, fused=True, device=device, rank=rank,
                                            nranks=nranks, global_ny=global_ny, y_offset=y_offset)
@@ -123,6 +124,17 @@ class StripSimulator:
     def from_global(cls, case: dict, state, rank: int, nranks: int, all_gather, device: int = 0, strict: bool = False):
         sub, sub_state, y0, _ = strip_case(case, state, rank, nranks)
         return cls(sub, sub_state, rank, nranks, case["ny"], y0, all_gather, device=device, strict=strict)
+
+    def close(self):
+        """Collective tear-down: every rank unmaps its peers' windows, then all ranks meet (the all-gather doubles as the
+        barrier), then the handle is destroyed -- freeing a window a peer still has mapped is undefined in CUDA IPC."""
+        if self.sim is None:
+            return
+        if self.nranks > 1:
+            self.sim._check(_lib.lib().swe_b200_close_peers(self.sim._h))
+            self._all_gather(b"closed")
+        self.sim.close()
+        self.sim = None
 
     def run_steps(self, n, maximum_timestep=None):
         self.sim.run_steps(n, maximum_timestep)
