@@ -244,6 +244,27 @@ def test_swashes_411_2d_config2_wet_variant(P):
     assert np.mean(np.abs(w[n // 2] - h_ref)) < 1.2e-5
 
 
+@pytest.mark.parametrize("strict", [False, True])
+def test_swashes_421_planar_surface_in_parabola_1d(P, oracle, strict):
+    """test/swashes.jl:75-86, 183-229: 1D, BottomTopography1D, moving shorelines, through the 1D embedding of the 2D kernels;
+    a tenth of the period (see cases.swashes421): strict == the oracle's genuine 1D path to 1e-13, analytic to 1.5x the
+    oracle's own error (4.8e-5)"""
+    case, st, period = cases.swashes421(256)
+    s = P.simulator_from_case(case, strict=strict)
+    o = oracle.OracleSim(case)
+    for x in (s, o):
+        x.set_state_interior(*st)
+    T = 0.1 * period
+    ns = P.simulate_to_time(s, T)
+    no = o.simulate_to_time(T)
+    w, hu = s.get_state_interior()
+    wo, huo = o.get_state_interior()
+    assert s.t == T and (ns == no or not strict)
+    assert cases.rel_linf(w, wo) <= (1e-13 if strict else 1e-9)
+    _, ref, _ = cases.swashes421(256, t=T)
+    assert np.mean(np.abs(w - ref[0])) < 1.5 * 4.8e-5
+
+
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_swashes_422b_planar_surface_in_paraboloid(P, dtype):
     """test/swashes.jl:106-119, 260-289: a planar free surface rotating in a paraboloid, moving shoreline, one rotation.

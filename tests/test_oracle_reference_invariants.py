@@ -436,3 +436,16 @@ def test_float32_mode_close_to_float64(O):
     assert out["float32"][0].dtype == np.float32
     for a, b in zip(out["float32"], out["float64"]):
         assert cases.rel_linf(a, b) < 5e-5
+
+
+def test_swashes_421_short_run_against_analytic(oracle):
+    """test/swashes.jl:75-86, 183-229 (1D planar surface in a parabola): the oracle's 1D path against the analytic solution
+    after a tenth of the period; freezes the error level the GPU test compares with (4.8e-5)"""
+    case, st, period = cases.swashes421(256)
+    o = oracle.OracleSim(case)
+    o.set_state_interior(*st)
+    o.simulate_to_time(0.1 * period)
+    w, hu = o.get_state_interior()
+    _, ref, _ = cases.swashes421(256, t=0.1 * period)
+    err = float(np.mean(np.abs(w - ref[0])))
+    assert 2e-5 < err < 6e-5, err

@@ -223,7 +223,7 @@ public:
         q.cutoff = (float)c.depth_cutoff; q.kappa = (float)c.kappa; q.constB = (float)c.const_B;
         q.theta = s2(c.theta); q.hith = s2(0.5 / c.theta); q.half = s2(0.5); q.mhalf = s2(-0.5); q.quarter = s2(0.25);
         q.g = s2(c.g); q.K = s2(0.5 * c.rho * c.g); q.i2k = s2(1.0 / (2 * c.kappa)); q.hk = s2(c.kappa / 2.0);
-        q.rho = s2(c.rho); q.nrdx = s2(-1.0 / dx); q.nrdy = s2(-1.0 / dy);
+        q.rho = s2(c.rho); q.nrdx = s2(-1.0 / dx); q.nrdy = s2(-1.0 / dy); q.prdy = s2(1.0 / dy);
         q.botx = s2(c.has_bottom_source ? -0.25 * c.g / dx : 0.0); q.boty = s2(c.has_bottom_source ? -0.25 * c.g / dy : 0.0); q.Cz = s2(c.Cz);
         q.rows = 126;
         if (const char* e = std::getenv("SWE_B200_X2_ROWS")) q.rows = std::max(3, atoi(e) / 3 * 3);   // multiple of 3

@@ -185,13 +185,13 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
         load_row(ja, bcell_of(2), q1, un0);
         S Lt[3], Rp[3];
         // cell ja-1 (only its right/upper face value is needed)
-        recon_cell<P, RECON, false, STAGE == 1>(p, qm, q0, q1, bface_y(1), bface_y(2), bcell_of(1), Lt, Rp);
+        recon_cell<P, RECON, false, false>(p, qm, q0, q1, bface_y(1), bface_y(2), bcell_of(1), Lt, Rp);
         // shift corners so that ca[0] = row ja-1, then load row ja+2 -> needed for bcell(ja+1)
         ca[0] = ca[1]; cb[0] = cb[1]; ca[1] = ca[2]; cb[1] = cb[2]; ca[2] = ca[3]; cb[2] = cb[3];
         load_corners(ja + 2, ca[3], cb[3]);
         load_row(ja + 1, bcell_of(2), q2, un1);
         // cell ja
-        recon_cell<P, RECON, false, STAGE == 1>(p, q0, q1, q2, bface_y(1), bface_y(2), bcell_of(1), Ly0, Ry0);
+        recon_cell<P, RECON, false, false>(p, q0, q1, q2, bface_y(1), bface_y(2), bcell_of(1), Ly0, Ry0);
         C s;
         central_upwind<P, false, 1, true>(p, Rp, Ly0, Gl, s);
         if (out_lane) msy = (S)s;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
             const C Blx = HASB ? (C)0.5 * (ca[0] + ca[1]) : p.constB;
             const C Brx = HASB ? (C)0.5 * (cb[0] + cb[1]) : p.constB;
             S Lx[3], Rx[3], Ln[3];
-            recon_cell<P, RECON, false, STAGE == 1>(p, ql, q0, qr, Blx, Brx, bcell_of(0), Lx, Rx);
+            recon_cell<P, RECON, false, false>(p, ql, q0, qr, Blx, Brx, bcell_of(0), Lx, Rx);
 #pragma unroll
             for (int k = 0; k < 3; ++k) Ln[k] = shfl_dn1(Lx[k]);      // left face value of cell i+1
             C F[3], s;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
         // ================= y direction (cell j, faces j-1/2 and j+1/2) =================
         {
             S Ly1[3], Ry1[3];
-            recon_cell<P, RECON, false, STAGE == 1>(p, q0, q1, q2, bface_y(1), bface_y(2), bcell_of(1), Ly1, Ry1);   // cell j+1
+            recon_cell<P, RECON, false, false>(p, q0, q1, q2, bface_y(1), bface_y(2), bcell_of(1), Ly1, Ry1);   // cell j+1
             C G[3], s;
             central_upwind<P, false, 1, true>(p, Ry0, Ly1, G, s);           // face j+1/2
             if (STAGE == 1 && out_lane) msy = (S)mx((C)msy, s);

@@ -82,7 +82,7 @@ struct Par2 {
     int rain_kind, infil_kind, infil_first, rows;
     int nitems;                   // work items of one launch (Args2::items)
     float cutoff, kappa, constB;
-    f2 theta, hith /*0.5/theta*/, half, mhalf, quarter, g, K /*0.5 rho g*/, i2k, hk, rho, nrdx, nrdy, botx, boty, Cz;
+    f2 theta, hith /*0.5/theta*/, half, mhalf, quarter, g, K /*0.5 rho g*/, i2k, hk, rho, nrdx, nrdy, prdy /*+1/dy*/, botx, boty, Cz;
 };
 
 struct Args2 {
@@ -616,6 +616,8 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
         f2 s = sp(0.0f);
         Gl[0] = Gl[1] = Gl[2] = sp(0.0f);
         if (__any_sync(0xffffffffu, any_wet(p, Rp[0], Ly0[0]))) cu2<1, STAGE == 1>(p, Rp, Ly0, Gl, s);   // face ja-1/2
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Gl[k] = mul(p.prdy, Gl[k]);          // carried scaled: Gl = (1/dy) * G(lower face)
         if (STAGE == 1 && out_pair) msy = fmaxf(msy, fmaxf(s.x, s.y));
         hsy = add(Ly0[0], Ry0[0]);
         Ej = c[2];
@@ -709,7 +711,9 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
             for (int k = 0; k < 3; ++k) {
                 const float Fp = __shfl_up_sync(0xffffffffu, F[k].y, 1);          // face (i-1 | i)
                 const f2 dF = mk(F[k].x - Fp, F[k].y - F[k].x);
-                dU[k] = fma2(p.nrdy, sub(G[k], Gl[k]), mul(p.nrdx, dF));
+                // -(1/dy)(G - G_lower) - (1/dx) dF with G_lower carried as (1/dy) G: the carried value dies in the inner fma,
+                // so the new one (end of the row) needs no register copy
+                dU[k] = fma2(p.nrdy, G[k], fma2(p.nrdx, dF, Gl[k]));
             }
             if (HASB) {
                 dU[1] = fma2(mul(p.botx, sub(tBr, tBl)), add(Lx[0], Rx[0]), dU[1]);
@@ -724,7 +728,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 dprev[k] = (TC && RECON) ? tfw[k] : fwd[k];
-                Ry0[k] = Ry1[k]; Gl[k] = G[k];
+                Ry0[k] = Ry1[k]; Gl[k] = mul(p.prdy, G[k]);
             }
             hsy = add(Ly1[0], Ry1[0]);
             // ================= store =================

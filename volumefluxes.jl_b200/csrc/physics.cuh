@@ -237,8 +237,9 @@ __device__ __forceinline__ C minmod3(C a, C b, C c) {
 }
 // ALT (fast Float64 only): the same value with 3 compare-and-selects instead of 6 --
 //   sign(f) * min(theta * min(|f|,|b|), (|f|+|b|)/2) if f and b have the same sign, else 0
-// (theta * x is monotone, so theta * min = min of the products; |f|+|b| = |f+b| for equal signs).  Measured on the
-// Float64 stage kernels: stage 1 -4.6 %, stage 2 +6.6 % (register allocation), so only stage 1 selects it.
+// (theta * x is monotone, so theta * min = min of the products; |f|+|b| = |f+b| for equal signs).  Round 1 selected it in
+// stage 1 of the generic Float64 kernel; since round 2 the fast Float64 policy runs on kernels_fused_d1.cuh (whose slope()
+// is this formula) and the generic kernels use ONE limiter form everywhere (ALT = false at every call site).
 template <class P, bool ALT = false>
 __device__ __forceinline__ typename P::C minmod_slope(typename P::S l, typename P::S c, typename P::S r,
                                                       typename P::C theta) {
