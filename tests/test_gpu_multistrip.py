@@ -59,17 +59,22 @@ def test_strips_match_single_domain_bitwise(P, oracle, name, dtype, nstrips):
             assert np.array_equal(a, b)
 
 
-def test_fast_strips_match_single_domain(P):
-    """fast arithmetic: a strip run executes exactly the same per-cell instruction sequence as the
-    single-domain run, so the results are bitwise equal here too"""
-    case, state = CASES["lake_wall_rk2"]("float32")
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("name,nstrips", [("lake_wall_rk2", 4), ("dry_periodic_rk2", 3), ("urban_norecon", 2), ("terrain_wall_fe", 3)])
+def test_fast_strips_match_single_domain(P, name, nstrips, dtype):
+    """fast arithmetic (the packed Float32 x2 kernels, the Float64 d1 kernels): a strip run executes exactly the same
+    per-cell instruction sequence as the single-domain run, so the results are bitwise equal here too"""
+    case, state = CASES[name](dtype)
+    mts = case.get("maximum_timestep")
     single = P.simulator_from_case(case)
     single.set_state_interior(*state)
-    single.run_steps(30)
-    grp = P.multigpu.LocalStripGroup(case, state, devices_for(4))
-    grp.run_steps(30)
+    single.run_steps(30, mts)
+    grp = P.multigpu.LocalStripGroup(case, state, devices_for(nstrips))
+    assert {s.kernel_family() for s in grp.sims} == {single.kernel_family()} <= {"fused-x2", "fused-d1"}
+    grp.run_steps(30, mts)
     for a, b in zip(grp.gather_interior(), single.get_state_interior()):
         assert np.array_equal(a, b)
+    assert grp.t == single.t and grp.dt == single.dt
 
 
 def test_cost_balanced_strips_bitwise(P):
