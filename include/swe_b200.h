@@ -200,6 +200,13 @@ int swe_b200_open_peers(swe_b200_handle* h, const void* all_blobs128);
  * sense on it. */
 int swe_b200_close_peers(swe_b200_handle* h);
 
+/* y-strips only.  Under PeriodicBC the first / last strip's low / high ghost rows -- and under NeumannBC the first strip's low
+ * ghost rows (bc.jl:56) -- are an image of cell rows at the OTHER end of the domain and arrive by exchange; stage 2 rebuilds
+ * U^1 in them and needs the bathymetry of those source cells.  `rows` = their (gc + 1) x (nx + 2gc + 1) corner values
+ * (side 0: the corner rows of the top gc interior cell rows of the global domain, side 1: of the bottom gc interior rows),
+ * element type cfg.dtype.  Required before the first step of such a strip when cfg.has_bathymetry. */
+int swe_b200_set_wrap_bathymetry(swe_b200_handle* h, int side, const void* rows, int64_t n_elems);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 /* Runs n steps like run_steps and returns the device time (CUDA events on the handle's stream)
  * of the whole region and of the dominant stage kernels, plus the number of kernels launched. */

@@ -28,6 +28,8 @@ CASES = {
     "dry_periodic_rk2": lambda dt: cases.dry_states_2d(dtype=dt, n=64),
     "terrain_wall_fe": lambda dt: cases.terrain_case(n=72, dtype=dt, level=0.0, wavelength=48.0, friction="bh2021", stepper="fe"),
     "urban_norecon": lambda dt: cases.urban_case(n=80, dtype=dt, level=0.5, wavelength=64.0),
+    # periodic wrap-around WITH bathymetry: the first / last strips rebuild their ghost rows with the bathymetry of the far end
+    "terrain_periodic_rk2": lambda dt: cases.terrain_case(n=72, dtype=dt, bc="periodic", level=0.0, wavelength=48.0, friction="bh2021"),
 }
 
 
@@ -60,7 +62,8 @@ def test_strips_match_single_domain_bitwise(P, oracle, name, dtype, nstrips):
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
-@pytest.mark.parametrize("name,nstrips", [("lake_wall_rk2", 4), ("dry_periodic_rk2", 3), ("urban_norecon", 2), ("terrain_wall_fe", 3)])
+@pytest.mark.parametrize("name,nstrips", [("lake_wall_rk2", 4), ("dry_periodic_rk2", 3), ("urban_norecon", 2), ("terrain_wall_fe", 3),
+                                          ("terrain_periodic_rk2", 3)])
 def test_fast_strips_match_single_domain(P, name, nstrips, dtype):
     """fast arithmetic (the packed Float32 x2 kernels, the Float64 d1 kernels): a strip run executes exactly the same
     per-cell instruction sequence as the single-domain run, so the results are bitwise equal here too"""

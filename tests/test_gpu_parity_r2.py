@@ -387,10 +387,25 @@ def test_close_peers_then_destroy(P):
         s.close()
 
 
-def test_neumann_multi_strip_is_refused(P):
-    case, state = _neumann("lake_bh2021", "float32")
-    with pytest.raises(P.B200Error):
-        P.multigpu.LocalStripGroup(case, state, [0, 0])
+@pytest.mark.parametrize("strict,dtype", [(True, "float64"), (True, "float32"), (False, "float32"), (False, "float64")])
+@pytest.mark.parametrize("name,nstrips", [("terrain_rk2", 3), ("terrain_fe_dry", 2), ("urban_norecon", 4), ("lake_bh2021", 2)])
+def test_neumann_strips_match_single_domain_bitwise(P, name, nstrips, strict, dtype):
+    """NeumannBC on y-strips: the low-y ghosts of the first strip are the image of the LAST strip's top rows (a
+    one-directional wrap-around push), the high-y ghosts evolve on the last strip, the high-x ghost column on every strip"""
+    import torch
+    case, state = _neumann(name, dtype)
+    mts = case.get("maximum_timestep")
+    single = P.simulator_from_case(case, strict=strict)
+    single.set_state_interior(*state)
+    single.run_steps(20, mts)
+    ref = single.get_state_interior()
+    nd = torch.cuda.device_count()
+    devs = list(range(nstrips)) if nd >= nstrips else [0] * nstrips
+    grp = P.multigpu.LocalStripGroup(case, state, devs, strict=strict)
+    grp.run_steps(20, mts)
+    for a, b in zip(grp.gather_interior(), ref):
+        assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
+    assert grp.t == single.t and grp.dt == single.dt
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -51,6 +51,7 @@ SYMBOLS = {
     "swe_b200_sync": (_i, [_vp]),
     "swe_b200_set_bathymetry": (_i, [_vp, _vp, _i64]),
     "swe_b200_set_rain_plane": (_i, [_vp, _vp, _i64]),
+    "swe_b200_set_wrap_bathymetry": (_i, [_vp, _i, _vp, _i64]),
     "swe_b200_set_infiltration_factor": (_i, [_vp, _vp, _i64]),
     "swe_b200_set_state_interior": (_i, [_vp, _vp, _vp, _vp]),
     "swe_b200_get_state_interior": (_i, [_vp, _vp, _vp, _vp]),

@@ -496,6 +496,11 @@ class Simulator:
             self._frain_y = grid.extent[2] + dy * (np.arange(1, self.Ny + 1) - 0.5 - gc + y_offset)
             self._refresh_rain(float(t0))
 
+    def set_wrap_bathymetry(self, side: int, corner_rows):
+        """y-strips: corner values of the gc image-source cell rows at the far end of the domain (swe_b200_set_wrap_bathymetry)"""
+        rows = np.ascontiguousarray(corner_rows, dtype=self.dtype)
+        self._check(_lib.lib().swe_b200_set_wrap_bathymetry(self._h, int(side), _ptr(rows), rows.size))
+
     def _check(self, rc):
         if rc != 0:
             _raise(rc, self._h)
@@ -944,5 +949,9 @@ def simulator_from_case(case: dict, strict: bool = False, fused: bool = True, de
     friction = ImplicitFriction(Cz=case.get("Cz", 0.03 ** 2), friction_function=fr) if fr else None
     system = ConservedSystem(backend, rec, CentralUpwind(eq), eq, grid, sources, friction)
     stepper = RungeKutta2() if case.get("stepper", "rk2") == "rk2" else ForwardEulerStepper()
-    return Simulator(backend, system, stepper, grid, cfl=case.get("cfl", 0.25), t0=case.get("t0", 0.0),
-                     rank=rank, nranks=nranks, global_ny=global_ny, y_offset=y_offset)
+    sim = Simulator(backend, system, stepper, grid, cfl=case.get("cfl", 0.25), t0=case.get("t0", 0.0),
+                    rank=rank, nranks=nranks, global_ny=global_ny, y_offset=y_offset)
+    for side, key in ((0, "wrap_B_lo"), (1, "wrap_B_hi")):        # y-strips with wrap-around ghost rows (multigpu.strip_case)
+        if case.get(key) is not None:
+            sim.set_wrap_bathymetry(side, case[key])
+    return sim

@@ -68,6 +68,7 @@ const char* swe_b200_last_error(swe_b200_handle* h) {
 int swe_b200_sync(swe_b200_handle* h) { FWD(sync()); }
 int swe_b200_set_bathymetry(swe_b200_handle* h, const void* B, int64_t n) { FWD(set_bathymetry(B, n)); }
 int swe_b200_set_infiltration_factor(swe_b200_handle* h, const double* f, int64_t n) { FWD(set_infiltration_factor(f, n)); }
+int swe_b200_set_wrap_bathymetry(swe_b200_handle* h, int side, const void* rows, int64_t n) { FWD(set_wrap_bathymetry(side, rows, n)); }
 int swe_b200_set_rain_plane(swe_b200_handle* h, const double* r, int64_t n) { FWD(set_rain_plane(r, n)); }
 int swe_b200_set_state_interior(swe_b200_handle* h, const void* w, const void* hu, const void* hv) { FWD(set_state_interior(w, hu, hv)); }
 int swe_b200_get_state_interior(swe_b200_handle* h, void* w, void* hu, void* hv) { FWD(get_state_interior(w, hu, hv)); }

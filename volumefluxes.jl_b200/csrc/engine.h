@@ -16,6 +16,7 @@ struct Engine {
     virtual int set_bathymetry(const void* B, int64_t n) = 0;
     virtual int set_infiltration_factor(const double* f, int64_t n) = 0;
     virtual int set_rain_plane(const double* r, int64_t n) = 0;
+    virtual int set_wrap_bathymetry(int side, const void* rows, int64_t n) = 0;
     virtual int set_state_interior(const void* w, const void* hu, const void* hv) = 0;
     virtual int get_state_interior(void* w, void* hu, void* hv) = 0;
     virtual int set_state_full(int buffer, const void* data) = 0;

@@ -58,6 +58,8 @@ public:
     S* vol[3] = {nullptr, nullptr, nullptr};
     S *left = nullptr, *right = nullptr, *ws = nullptr;
     S* B = nullptr;
+    S* wrapC = nullptr;     // [2 sides][gc + 1 corner rows][Bp]: bathymetry of the wrap-around image's source rows (y-strips)
+    bool wrap_set[2] = {false, false};
     double* factor = nullptr;
     double* rainp = nullptr;     // FunctionalRain values per cell (rain_kind == SWE_B200_RAIN_PLANE)
     Ctl* ctl = nullptr;
@@ -78,7 +80,8 @@ public:
     long long peer_Ny[MAX_RANKS] = {}, peer_plane[MAX_RANKS] = {}, peer_vol_bytes[MAX_RANKS] = {};
     Mailbox* peer_mbox[MAX_RANKS] = {};
     bool peer_ipc[MAX_RANKS] = {};
-    int lo_rank = -1, hi_rank = -1;
+    int lo_rank = -1, hi_rank = -1;   // ranks my bottom / top owned rows are pushed to (-1: nobody)
+    bool recv_lo = false, recv_hi = false;   // do my bottom / top ghost rows come from a neighbour?
     unsigned long long xseq = 0;        // halo exchange stamp counter (identical on all ranks)
     unsigned long long sseq = 0;        // step sequence for the CFL all-gather
     unsigned long long pending_U = 0;   // stamp of the last U exchange the next K1 must wait for
@@ -136,7 +139,7 @@ public:
         // y boundaries of this strip are physical unless a neighbouring rank owns the rows beyond
         // (periodic-y across ranks is an exchange between rank 0 and rank P-1)
         const bool multi = c.nranks > 1;
-        par.ylo_phys = (!multi || (c.rank == 0 && c.bc != SWE_B200_BC_PERIODIC)) ? 1 : 0;
+        par.ylo_phys = (!multi || (c.rank == 0 && c.bc != SWE_B200_BC_PERIODIC && c.bc != SWE_B200_BC_NEUMANN)) ? 1 : 0;
         par.yhi_phys = (!multi || (c.rank == c.nranks - 1 && c.bc != SWE_B200_BC_PERIODIC)) ? 1 : 0;
         vol_bytes = (sizeof(S) * plane * 3 + 255) / 256 * 256;
         mbox_offset = 3 * vol_bytes;
@@ -149,9 +152,14 @@ public:
         static_assert(sizeof(Mailbox) <= 768, "mailbox too large");
         if (multi) {
             if (c.nranks > MAX_RANKS) { err = "at most 8 ranks"; return SWE_B200_EUNSUPPORTED; }
-            const bool per = c.bc == SWE_B200_BC_PERIODIC;
+            const bool per = c.bc == SWE_B200_BC_PERIODIC, neu = c.bc == SWE_B200_BC_NEUMANN;
+            // periodic: the first / last strips are neighbours too.  NeumannBC (bc.jl:56-58): the low-y ghosts of the
+            // domain are the image of its TOP interior rows -- a one-directional wrap-around from the last strip to the
+            // first -- and its high-y ghosts evolve on their own on the last strip (k_neumann_*): nothing comes back.
             lo_rank = c.rank > 0 ? c.rank - 1 : (per ? c.nranks - 1 : -1);
-            hi_rank = c.rank < c.nranks - 1 ? c.rank + 1 : (per ? 0 : -1);
+            hi_rank = c.rank < c.nranks - 1 ? c.rank + 1 : ((per || neu) ? 0 : -1);
+            recv_lo = c.rank > 0 || per || neu;
+            recv_hi = c.rank < c.nranks - 1 || per;
         }
         if (c.has_bathymetry) {
             SWE_CUDA(cudaMalloc(&B, sizeof(S) * (size_t)Bp * (Ny + 1)));
@@ -176,9 +184,7 @@ public:
         for (int q = 0; q < 16; ++q) { rt.rates[q] = c.rain_rates[q]; rt.times[q] = c.rain_times[q]; }
         ip.kind = c.infil_kind; ip.cst = c.infil_const; ip.f0 = c.f0; ip.fc = c.fc; ip.k = c.k;
         // the fused stage kernels cover the practical 2D SWE with gc == 2 and periodic / wall BCs
-        // (NeumannBC: single strip only -- its low-y ghosts are images of the TOP interior rows and its high-y ghosts evolve
-        // on their own, kernels_fused.cuh k_neumann_*; a y-strip version would need a one-directional wrap-around exchange)
-        fused_ok = c.fused && c.eq_kind == 0 && gc == 2 && c.nx >= 4 && c.ny >= 4 && !(c.bc == SWE_B200_BC_NEUMANN && multi);
+        fused_ok = c.fused && c.eq_kind == 0 && gc == 2 && c.nx >= 4 && c.ny >= 4;
         setup_x2(c);
         setup_d1(c);
         if (multi && !fused_ok) {
@@ -193,7 +199,7 @@ public:
         for (int r = 0; r < MAX_RANKS; ++r)
             if (peer_ipc[r] && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
         cudaFree(slab);
-        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(factor); cudaFree(rainp); cudaFree(ctl); cudaFree(d_items[0]); cudaFree(d_items[1]); cudaFree(diag_buf);
+        cudaFree(left); cudaFree(right); cudaFree(ws); cudaFree(B); cudaFree(wrapC); cudaFree(factor); cudaFree(rainp); cudaFree(ctl); cudaFree(d_items[0]); cudaFree(d_items[1]); cudaFree(diag_buf);
         if (h_ctl) cudaFreeHost(h_ctl);
         for (auto e : ev) cudaEventDestroy(e);
         cudaFree(snap);
@@ -259,7 +265,7 @@ public:
     void launch_stage_d1(const S* U, const S* D, S* out) {
         if constexpr (std::is_same<P, Policy<double, double, false>>::value) {
             d1::Args1 a;
-            a.p = par1; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl; a.items = d_items[STAGE - 1];
+            a.p = par1; a.U = U; a.D = D; a.out = out; a.B = B; a.wrapLo = wrap_ptr(0); a.wrapHi = wrap_ptr(1); a.factor = factor; a.ctl = ctl; a.items = d_items[STAGE - 1];
             a.p.nitems = n_items[STAGE - 1];
             const int items = n_items[STAGE - 1];
             dim3 g(std::min((items + d1::WPB - 1) / d1::WPB, 148 * d1::minb<STAGE>()));
@@ -377,7 +383,7 @@ public:
     void launch_stage_x2(const S* U, const S* D, S* out) {
         if constexpr (std::is_same<P, Policy<float, float, false>>::value) {
             x2::Args2 a;
-            a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.factor = factor; a.ctl = ctl; a.items = d_items[STAGE - 1];
+            a.p = par2; a.U = U; a.D = D; a.out = out; a.B = B; a.wrapLo = wrap_ptr(0); a.wrapHi = wrap_ptr(1); a.factor = factor; a.ctl = ctl; a.items = d_items[STAGE - 1];
             a.p.nitems = n_items[STAGE - 1];
             // persistent warps pulling (tile, rows) items: at most 4 blocks per SM are resident (128 registers)
             const int items = n_items[STAGE - 1];
@@ -448,6 +454,31 @@ public:
         SWE_CUDA(cudaStreamSynchronize(stream));
         return SWE_B200_OK;
     }
+    // y-strips whose ghost rows are a wrap-around image (first strip under periodic / NeumannBC, last strip under periodic):
+    // stage 2 rebuilds U^1 in those rows from the exchanged (U, dU) rows and needs the bathymetry of the SOURCE cells, which
+    // live at the other end of the domain.  The host hands over their gc + 1 corner rows once.
+    bool needs_wrap(int side) const {
+        if (cfg.nranks <= 1 || !cfg.has_bathymetry) return false;
+        const bool per = cfg.bc == SWE_B200_BC_PERIODIC, neu = cfg.bc == SWE_B200_BC_NEUMANN;
+        return side == 0 ? (cfg.rank == 0 && (per || neu)) : (cfg.rank == cfg.nranks - 1 && per);
+    }
+    int set_wrap_bathymetry(int side, const void* rows, int64_t n) override {
+        if (side < 0 || side > 1 || !needs_wrap(side)) { err = "this strip has no wrap-around ghost rows with bathymetry on that side"; return SWE_B200_EINVAL; }
+        if (n != (int64_t)(gc + 1) * (Nx + 1)) {
+            err = "Wrap bathymetry should be of size (" + std::to_string(Nx + 1) + ", " + std::to_string(gc + 1) + ")";
+            return SWE_B200_EDOMAIN;
+        }
+        if (!wrapC) {
+            SWE_CUDA(cudaMalloc(&wrapC, sizeof(S) * (size_t)Bp * (gc + 1) * 2));
+            SWE_CUDA(cudaMemsetAsync(wrapC, 0, sizeof(S) * (size_t)Bp * (gc + 1) * 2, stream));
+        }
+        SWE_CUDA(cudaMemcpy2DAsync(wrapC + (size_t)side * (gc + 1) * Bp, sizeof(S) * Bp, rows, sizeof(S) * (Nx + 1), sizeof(S) * (Nx + 1),
+                                   gc + 1, cudaMemcpyHostToDevice, stream));
+        SWE_CUDA(cudaStreamSynchronize(stream));
+        wrap_set[side] = true;
+        return SWE_B200_OK;
+    }
+    const S* wrap_ptr(int side) const { return wrap_set[side] ? wrapC + (size_t)side * (gc + 1) * Bp : nullptr; }
     int set_rain_plane(const double* r, int64_t n) override {
         if (cfg.rain_kind != SWE_B200_RAIN_PLANE) { err = "no FunctionalRain (rain_kind = SWE_B200_RAIN_PLANE) configured"; return SWE_B200_EINVAL; }
         if (n != plane) {
@@ -724,7 +755,7 @@ public:
     template <int STAGE>
     void launch_stage(const S* U, const S* D, S* out) {
         StageArgs<P> a;
-        a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.Bp = Bp; a.factor = factor; a.rainp = rainp; a.ctl = ctl;
+        a.p = par; a.U = U; a.D = D; a.out = out; a.B = B; a.wrapLo = wrap_ptr(0); a.wrapHi = wrap_ptr(1); a.Bp = Bp; a.factor = factor; a.rainp = rainp; a.ctl = ctl;
         a.rain_kind = cfg.rain_kind; a.infil_kind = cfg.infil_kind; a.infil_first = cfg.infil_first;
         // rows marched per block: every block pays a ~4.5-row prologue, and the launch runs in waves of 148 x 4
         // resident blocks, so the rows are chosen to minimise waves x (rows + 4.5).  Large grids end up near 64; a
@@ -794,7 +825,7 @@ public:
         a.dt.enabled = with_dt ? 1 : 0;
         if (with_dt) {      // the last block of the push also gathers the maxima and computes dt (was k_ctl_dt_multi)
             a.dt.dx = par_dx(); a.dt.dy = par_dy(); a.dt.cfl = (double)(S)cfg.cfl;
-            a.dt.nranks = cfg.nranks; a.dt.has_lo = lo_rank >= 0; a.dt.has_hi = hi_rank >= 0;
+            a.dt.nranks = cfg.nranks; a.dt.has_lo = recv_lo; a.dt.has_hi = recv_hi;
             a.dt.seq = sseq; a.dt.dU_stamp = rows ? a.stamp : 0ull;
         }
         return a;
@@ -825,7 +856,7 @@ public:
         if (peers_open) {
             a.push = push_args(next, next_index, 2, false, true, false);
             a.nbp = push_blocks(a.push.rows);
-            a.has_lo = lo_rank >= 0; a.has_hi = hi_rank >= 0;
+            a.has_lo = recv_lo; a.has_hi = recv_hi;
             a.mb = mbox;
             nblocks += 6 * a.nbp;
         }
@@ -843,18 +874,19 @@ public:
         launch_stage<1>(U, nullptr, D);
         mark("K1");
         const bool rk2 = cfg.stepper == SWE_B200_RK2;
+        const bool neumann = cfg.bc == SWE_B200_BC_NEUMANN;
+        const int nline = (int)((Ny + Nx - 1 + 127) / 128);
+        if (neumann) {       // dU of the self-evolving outermost high ghost column / row = the per-cell sources (before the
+                             // dU rows go to the neighbours: their halo rows carry the ghost column too)
+            k_neumann_dU<P><<<nline, 128, 0, stream>>>(par, D, ctl, factor, rainp, cfg.rain_kind, cfg.infil_kind, cfg.infil_first);
+            ++launches;
+        }
         if (multi) {
             ++sseq;
             // dU rows (RK2 only) + this rank's CFL maxima; the same launch then gathers all maxima -> dt
             push_halo(D, cur[1], 0, true, rk2, true);
         } else {
             k_ctl_dt<S><<<1, 1, 0, stream>>>(ctl, par_dx(), par_dy(), (S)cfg.cfl);
-            ++launches;
-        }
-        const bool neumann = cfg.bc == SWE_B200_BC_NEUMANN;
-        const int nline = (int)((Ny + Nx - 1 + 127) / 128);
-        if (neumann) {       // dU of the self-evolving outermost high ghost column / row = the per-cell sources
-            k_neumann_dU<P><<<nline, 128, 0, stream>>>(par, D, ctl, factor, rainp, cfg.rain_kind, cfg.infil_kind, cfg.infil_first);
             ++launches;
         }
         mark("dt(+push dU)");
@@ -884,7 +916,7 @@ public:
         const BeginKey key{max_dt_host, t_end, max_timestep, use_t_end, match};
         if (peers_open && fused_ok && pending_U) {   // + wait for the neighbours' U rows of set_state_interior's exchange
             k_ctl_begin_multi<<<1, 1, 0, stream>>>(ctl, rt, ip, max_dt_host, use_t_end, match, t_end, max_timestep, mbox,
-                                                   lo_rank >= 0, hi_rank >= 0, pending_U);
+                                                   recv_lo, recv_hi, pending_U);
             pending_U = 0;
             ++launches;
         } else if (!(fused_ok && primed && primed_key == key)) {
@@ -896,6 +928,12 @@ public:
     }
     int prepare() {
         if (!fused_ok) return ensure_face_buffers();
+        for (int side = 0; side < 2; ++side)
+            if (needs_wrap(side) && !wrap_set[side]) {
+                err = "this strip's ghost rows are a wrap-around image of the far end of the domain: hand over the bathymetry of the "
+                      "source rows with swe_b200_set_wrap_bathymetry first";
+                return SWE_B200_EINVAL;
+            }
         return SWE_B200_OK;
     }
 

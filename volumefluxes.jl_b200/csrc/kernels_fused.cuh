@@ -41,6 +41,8 @@ struct StageArgs {
     const S* D;        // dU (stage 2 input)
     S* out;            // stage 1: dU ; stage 2: U^{n+1}
     const S* B;        // corners (pitch Bp) or nullptr
+    const S* wrapLo;   // y-strips whose low / high ghost rows are a wrap-around image (periodic, NeumannBC low side): the gc+1
+    const S* wrapHi;   // corner rows (pitch Bp) of the image's SOURCE cell rows; nullptr otherwise
     int Bp;
     const double* factor;   // Horton factor plane or nullptr
     const double* rainp;    // FunctionalRain values per cell or nullptr
@@ -153,8 +155,11 @@ __global__ void __launch_bounds__(FUSED_WPB * 32) k_stage(const StageArgs<P> a) 
 #pragma unroll
             for (int k = 0; k < 3; ++k) un[k] = u[k];
             C Bm = bc_actual;
-            if (HASB && (xs != ic || ys != j)) {
-                const S* r0 = a.B + (size_t)ys * Bp + xs;
+            // a ghost cell is rebuilt with the bathymetry of the cell the BC copies it from: (xs, ys) of this strip, or --
+            // where the ghost rows came from the far end of the domain by exchange -- the wrap rows handed over by the host
+            const S* wr = !HASB ? nullptr : (j < 2 ? a.wrapLo : (j >= Ny - 2 ? a.wrapHi : nullptr));
+            if (HASB && (xs != ic || ys != j || wr)) {
+                const S* r0 = wr ? wr + (size_t)(j < 2 ? j : j - (Ny - 2)) * Bp + xs : a.B + (size_t)ys * Bp + xs;
                 Bm = (C)0.25 * (r0[0] + r0[1] + r0[Bp] + r0[Bp + 1]);
             }
             substep_tail<P>(p, u, d, dt, dt_s, Bm, q);
@@ -349,7 +354,7 @@ __global__ void k_neumann_dU(Par<typename P::C> p, typename P::S* D, const Ctl* 
     using S = typename P::S;
     using C = typename P::C;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= (long long)p.Ny + p.Nx - 1) return;
+    if (t >= (long long)p.Ny + (p.yhi_phys ? p.Nx - 1 : 0)) return;     // the ghost ROW only where the high y side is physical
     int i, j;
     neumann_line_cell<P>(t, p.Nx, p.Ny, i, j);
     const size_t q = (size_t)j * p.Nx + i;
@@ -373,7 +378,7 @@ __global__ void k_neumann_ghosts(Par<typename P::C> p, Bathy<P> bt, const typena
     using S = typename P::S;
     using C = typename P::C;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= (long long)p.Ny + p.Nx - 1) return;
+    if (t >= (long long)p.Ny + (p.yhi_phys ? p.Nx - 1 : 0)) return;
     int i, j;
     neumann_line_cell<P>(t, p.Nx, p.Ny, i, j);
     const size_t q = (size_t)j * p.Nx + i;

@@ -86,6 +86,8 @@ struct Args1 {
     const R* D;
     R* out;
     const R* B;
+    const R* wrapLo;              // corner rows of the wrap-around image's source rows (see StageArgs), or nullptr
+    const R* wrapHi;
     const double* factor;
     Ctl* ctl;
     const int4* items;            // (tile, first interior row, number of rows (multiple of 3 except at the top), 0)
@@ -278,8 +280,9 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_d1(const Args1 a) {
             for (int k = 0; k < 3; ++k) q[k] = u[k];
         } else {
             R Bm = Bc_here;
-            if (HASB && (xghost || remapped)) {               // ghost: bathymetry of the source cell
-                const R* r0 = a.B + (size_t)ys * Bp + xs;
+            const R* wr = !HASB ? nullptr : (ys < 2 ? a.wrapLo : (ys >= Ny - 2 ? a.wrapHi : nullptr));   // (not remapped there: ys = row)
+            if (HASB && (xghost || remapped || wr)) {         // ghost: bathymetry of the source cell
+                const R* r0 = wr ? wr + (size_t)(ys < 2 ? ys : ys - (Ny - 2)) * Bp + xs : a.B + (size_t)ys * Bp + xs;
                 Bm = 0.25 * (r0[0] + r0[1] + r0[Bp] + r0[Bp + 1]);
             }
 #pragma unroll

@@ -91,6 +91,8 @@ struct Args2 {
     const float* D;
     float* out;
     const float* B;
+    const float* wrapLo;          // corner rows of the wrap-around image's source rows (see StageArgs), or nullptr
+    const float* wrapHi;
     const double* factor;
     Ctl* ctl;
     const int4* items;            // (tile, first interior row, number of rows (multiple of 3 except at the top), 0)
@@ -451,8 +453,10 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
             for (int k = 0; k < 3; ++k) q[k] = u[k];
         } else {
             f2 Bm = Bc_here;
-            if (!FASTROW && HASB && (xghost || remapped)) {          // ghost: bathymetry of the source cells
-                const float* r0 = a.B + (size_t)ys * Bp + xs;
+            // (halo rows only ever pass through the prologue / the generic trips: nothing is added to a FAST trip)
+            const float* wr = (decltype(fast_tag)::value || !HASB) ? nullptr : (ys < 2 ? a.wrapLo : (ys >= Ny - 2 ? a.wrapHi : nullptr));
+            if (!FASTROW && HASB && (xghost || remapped || wr)) {    // ghost: bathymetry of the source cells
+                const float* r0 = wr ? wr + (size_t)(ys < 2 ? ys : ys - (Ny - 2)) * Bp + xs : a.B + (size_t)ys * Bp + xs;
                 const float m = r0[1] + r0[Bp + 1];
                 Bm = mk(0.25f * (r0[0] + r0[Bp] + m), 0.25f * (m + r0[2] + r0[Bp + 2]));
             }

@@ -3,7 +3,8 @@
 The reference is single-device; this is the new capability BASELINE.json's config 5 asks for.
 One process per GPU (torchrun): every rank owns ny/P interior rows plus 2 ghost rows per side; the
 x-direction BC is local on every rank, the y-direction BC only on the first / last rank (periodic-y
-becomes an exchange between rank 0 and rank P-1).  The data path never touches the host: the stage
+becomes an exchange between rank 0 and rank P-1; NeumannBC's low-y image a one-directional push from rank P-1 to
+rank 0, with the far end's bathymetry rows handed over once: swe_b200_set_wrap_bathymetry).  The data path never touches the host: the stage
 kernels' neighbours push halo rows and CFL maxima into each other's memory over NVLink
 (csrc/kernels_exchange.cuh); torch.distributed is used ONLY to all-gather the 128-byte window
 descriptors once at start-up (and by tests / bench to gather results).
@@ -82,7 +83,15 @@ def strip_case(case: dict, state: Sequence[np.ndarray], rank: int, nranks: int, 
     sub["ny"] = n
     B = case.get("B")
     if B is not None and not np.isscalar(B):
-        sub["B"] = np.ascontiguousarray(np.asarray(B)[y0:y0 + n + 2 * gc + 1])
+        Bg = np.asarray(B)
+        sub["B"] = np.ascontiguousarray(Bg[y0:y0 + n + 2 * gc + 1])
+        # ghost rows that are a wrap-around image of the far end of the domain (periodic: both ends; NeumannBC: the low
+        # ghosts are the image of the top interior rows, bc.jl:56): stage 2 needs the bathymetry of the SOURCE cells
+        bc = case.get("bc", "periodic")
+        if nranks > 1 and rank == 0 and bc in ("periodic", "neumann"):
+            sub["wrap_B_lo"] = np.ascontiguousarray(Bg[ny:ny + gc + 1])              # corner rows of global cell rows ny .. ny+gc-1
+        if nranks > 1 and rank == nranks - 1 and bc == "periodic":
+            sub["wrap_B_hi"] = np.ascontiguousarray(Bg[gc:2 * gc + 1])              # corner rows of global cell rows gc .. 2gc-1
     infil = case.get("infiltration")
     if isinstance(infil, dict) and not np.isscalar(infil.get("factor", 1.0)):
         f = dict(infil)
