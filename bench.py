@@ -488,7 +488,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
                     help="BASELINE config (SURVEY 8d numbering): 5 = the bench line (16384^2 Float32); 2-4 = side measurements, N = 1")
-    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=None,
+                    help="grid size (use --size under torchrun, whose own parser finds --n ambiguous)")
     ap.add_argument("--dtype", default=None, choices=["float32", "float64"])
     ap.add_argument("--cpu-n", type=int, default=1024, dest="cpu_n")
     ap.add_argument("--cpu-rows", type=int, default=1024, dest="cpu_rows",
