@@ -43,11 +43,19 @@ constexpr int minb() { return STAGE == 2 ? D1_MINB2 : D1_MINB; }
 
 __device__ __forceinline__ R vmin(R a, R b) { return a < b ? a : b; }
 __device__ __forceinline__ R vmax(R a, R b) { return a > b ? a : b; }
-// The kernel is bound by the FP64 pipe (profiles/r02f_ncu_d1_f64_4096.txt: 62 % busy, the top pipe; DSETP runs there
-// too).  Comparisons whose operands are known to be non-negative, and tests against zero, are done on the bit patterns
-// by the integer ALU instead -- the ordering of non-negative doubles is the ordering of their bit patterns.
+// The FP64 pipe is the top pipe (profiles/r02f_ncu_d1_f64_4096.txt: 62 % busy; DSETP runs there too), but the kernel is issue-bound:
+// moving 64-bit comparisons to the integer ALU (two ISETP on the bit patterns of non-negative operands) relieves the pipe and
+// costs instructions -- measured slower (D1_HYBRID below).  What stays on the ALU are the tests that are a single integer
+// instruction: the sign bit (relu) and the exponent word (the normal-number test of sqrt_n).
 __device__ __forceinline__ R vmin_nn(R a, R b) { return __double_as_longlong(a) < __double_as_longlong(b) ? a : b; }
+#ifndef D1_HYBRID
+#define D1_HYBRID 3
+#endif
+#if D1_HYBRID >= 3
+__device__ __forceinline__ R vmax_nn(R a, R b) { return a > b ? a : b; }
+#else
 __device__ __forceinline__ R vmax_nn(R a, R b) { return __double_as_longlong(a) > __double_as_longlong(b) ? a : b; }
+#endif
 __device__ __forceinline__ R relu(R x) { return __double2hiint(x) < 0 ? 0.0 : x; }
 __device__ __forceinline__ R rcp_n(R x) {                // hardware seed (~2^-20) + two Newton steps: ~1 ulp
     R r;
@@ -96,10 +104,27 @@ struct Args1 {
 // ---- minmod-limited slope from the backward / forward differences (linearreconstruction.jl:28-43) ----------------
 __device__ __forceinline__ R slope(R theta, R b, R f) {
     const R af = fabs(f), ab = fabs(b);
+    // 64-bit comparisons: one DSETP on the FP64 pipe, or two ISETP on the integer ALU (non-negative operands).  D1_HYBRID: 0 =
+    // both minima on the ALU, 1 = the first on the FP64 pipe, 2 = both (sign / zero tests stay on the ALU), 3 = every 64-bit
+    // comparison on the FP64 pipe.  Measured (profiles/r02v_ab_d1_hybrid.txt): config 2 at 4096^2 0.696 / 0.684 / 0.666 ms/step
+    // for 0 / 1 / 2, 0.664 for 3 (the default) -- the kernel is issue-bound, so the fewer instructions win although the FP64 pipe is
+    // the busier one; only the tests that are ONE integer instruction (sign bit, exponent word) stay on the ALU.
+#if D1_HYBRID >= 1
+    const R m1 = vmin(af, ab);
+#else
     const R m1 = vmin_nn(af, ab);
+#endif
+#if D1_HYBRID >= 2
+    const R m2 = vmin(theta * m1, 0.5 * (af + ab));
+#else
     const R m2 = vmin_nn(theta * m1, 0.5 * (af + ab));
+#endif
     // equal strict signs, tested on the sign bits (a product f * b would underflow for tiny differences)
+#if D1_HYBRID >= 3
+    const bool same = ((__double2hiint(f) ^ __double2hiint(b)) >= 0) && m1 > 0.0;
+#else
     const bool same = ((__double2hiint(f) ^ __double2hiint(b)) >= 0) && __double_as_longlong(m1) != 0ll;
+#endif
     return same ? copysign(m2, f) : 0.0;
 }
 
@@ -140,11 +165,19 @@ __device__ __forceinline__ R desing_pos(const Par1& p, R h) {
 // (swe_2D.jl:43-81, equation.jl:40-62, centralupwind.jl:54-63) ----------------------------------------------------
 template <int DIR>
 __device__ __forceinline__ void side1(const Par1& p, R h, R hu, R hv, R F[3], R& ep, R& en) {
+#ifndef D1_MASKMUL
+#define D1_MASKMUL 0         // 1: hm = h * m (one DMUL) instead of the select (two SEL)
+#endif
     const bool wet = h > p.cutoff;
+    const R m = wet ? 1.0 : 0.0;
+#if D1_MASKMUL
+    const R hm = h * m;
+#else
     const R hm = wet ? h : 0.0;
+#endif
     const R pres = p.K * (hm * hm);
     const R c = sqrt_n(p.g * hm);
-    const R rm = rcp_n(desing_pos(p, hm)) * (wet ? 1.0 : 0.0);     // (a multiply, not a select: no branch around the Newton steps)
+    const R rm = rcp_n(desing_pos(p, hm)) * m;                     // (a multiply, not a select: no branch around the Newton steps)
     const R u = hu * rm, v = hv * rm;
     const R rh = p.rho * hm;
     R un;
