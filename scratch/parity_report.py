@@ -51,7 +51,9 @@ def small(out, checkpoints=(20, 25, 100), seeds=(1, 2, 3, 4)):
               "rel-L-inf per field (w / hu / hv; w against max|w|, momenta against max(|hu|,|hv|)), interior cells.\n"
               "`sens` = the ORACLE run from a +-1 ulp perturbed initial state against the oracle itself (max over "
               f"{len(seeds)} seeds): what the scheme does to the smallest input change Float32 can express.\n"
-              "`mask` = cells whose wet flag differs (CUDA fast vs oracle) / (perturbed oracle vs oracle, max over seeds).\n\n"
+              "`mask` = cells whose wet flag differs (CUDA fast vs oracle) / (perturbed oracle vs oracle, max over seeds).\n"
+              "`err / max(1e-5, sens)`: w against its own sensitivity, both momenta against the larger of the two momentum sensitivities "
+              "(they share one scale; per field the sensitivity of four seeds is heavy-tailed).\n\n"
               "| case | steps | fast vs oracle | oracle 1-ulp sens | err / max(1e-5, sens) | mask | dt rel err | strict vs oracle |\n"
               "|---|---|---|---|---|---|---|---|\n")
     worst = 0.0
@@ -76,7 +78,8 @@ def small(out, checkpoints=(20, 25, 100), seeds=(1, 2, 3, 4)):
             st = interior(sims["strict"].get_state_full())
             err = cases.field_errors(a, b)
             sens = np.max([cases.field_errors(pp[n], b) for pp, _ in pert], axis=0)
-            ratio = max(e / max(1e-5, sn) for e, sn in zip(err, sens))
+            sens_m = max(sens[1], sens[2])          # the two momenta share one scale and one yardstick (heavy-tailed per field)
+            ratio = max(e / max(1e-5, sn) for e, sn in zip(err, (sens[0], sens_m, sens_m)))
             worst = max(worst, ratio)
             mism = int(np.sum(wet_mask(case, a[0]) != wet_mask(case, b[0])))
             mism_ref = max(int(np.sum(wet_mask(case, pp[n][0]) != wet_mask(case, b[0]))) for pp, _ in pert)
@@ -127,7 +130,8 @@ def full(out, sizes):
             cp = pert.compare_states(strict, tol=tol)
             c10 = fast.compare_states(strict, tol=10 * tol)["cells_over_tol"]
             cp10 = pert.compare_states(strict, tol=10 * tol)["cells_over_tol"]
-            ratio = max(e / max(tol, sn) for e, sn in zip(c["rel_linf"], cp["rel_linf"]))
+            sm = max(cp["rel_linf"][1], cp["rel_linf"][2])
+            ratio = max(e / max(tol, sn) for e, sn in zip(c["rel_linf"], (cp["rel_linf"][0], sm, sm)))
             ddt = abs(fast.dt - strict.dt) / strict.dt
             out.write(f"| {label} ({fast.kernel_family()}) | {n}x{n} {dtype} | {n_steps} | {fmt(c['rel_linf'])} | {fmt(cp['rel_linf'])} | "
                       f"{ratio:.2f} | {c['mask_mismatch']} / {cp['mask_mismatch']} (of {c['wet_other']}) | "

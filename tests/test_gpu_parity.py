@@ -172,7 +172,10 @@ def test_fast_fused_parity_100_steps(P, oracle, name, dtype, tol):
         err = cases.field_errors(a, b)
         print(f"\n{name} {dtype} N={n}: err {['%.1e' % e for e in err]} "
               f"oracle 1-ulp sensitivity {['%.1e' % e for e in sens]}")
-        for e, sn, nm in zip(err, sens, ("w", "hu", "hv")):
+        # the two momenta share one scale (max(|hu|, |hv|)) and one yardstick: per field the sensitivity of four seeds is too
+        # heavy-tailed (thin-film run-off at 100 steps: hu 4e-3, hv 1.3e-1 -- the same dry-state switch, seen in one field)
+        sens_y = [sens[0], max(sens[1], sens[2]), max(sens[1], sens[2])]
+        for e, sn, nm in zip(err, sens_y, ("w", "hu", "hv")):
             assert e <= max(tol, 4 * sn), \
                 f"N={n} {nm}: rel L-inf {e:.3e} (tolerance {tol:g}, 1-ulp sensitivity {sn:.3e})"
         err_dt = float(np.max(np.abs(np.array(dts) - dts_o[:n]) / dts_o[:n]))

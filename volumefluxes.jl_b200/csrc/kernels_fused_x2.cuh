@@ -143,7 +143,7 @@ __device__ __forceinline__ void recon2(const Par2& p, const f2 c[3], const f2 bw
 // argument of cell j+1 is the forward one of cell j (one FMUL2 per variable and row less); the central
 // difference is rebuilt as (0.5/theta) * (tf + tb).
 #ifndef X2_TCARRY
-#define X2_TCARRY 2          // bit 0: stage 1, bit 1: stage 2
+#define X2_TCARRY 3          // bit 0: stage 1, bit 1: stage 2 (round 2: stage 1 too, K1 -1.7 %; round 1 it cost registers there)
 #endif
 #ifndef X2_NOGHOST_FAST
 #define X2_NOGHOST_FAST 0    // 1: warps holding x-ghost pairs never take the FAST trips (which then drop the ghost code)
