@@ -59,17 +59,30 @@ struct DtArgs {
     int enabled, nranks, has_lo, has_hi;
     unsigned long long seq, dU_stamp;
 };
+// Called by the first warp of the last block (all 32 lanes): lane r waits for rank r's stamp and reads its two maxima -- the
+// 3 x nranks dependent loads of a one-thread loop (each an uncached read of peer-written memory) collapse into 3 -- then a
+// warp max; lane 0 finishes the time step.  The maximum is order-independent, so every rank still computes identical bits.
 template <class S>
 __device__ __forceinline__ void ctl_dt_multi(Ctl* c, Mailbox* mb, const DtArgs& d) {
     const int par = (int)(d.seq & 1ull);
+    const int lane = threadIdx.x & 31;
     unsigned long long bx = 0ull, by = 0ull;
-    for (int r = 0; r < d.nranks; ++r) {
-        spin_until(&mb->speed_stamp[par][r], d.seq, mb);
-        const unsigned long long x = *(volatile unsigned long long*)&mb->speed[par][r][0];
-        const unsigned long long y = *(volatile unsigned long long*)&mb->speed[par][r][1];
-        bx = x > bx ? x : bx;
-        by = y > by ? y : by;
+    if (lane < d.nranks) {
+        spin_until(&mb->speed_stamp[par][lane], d.seq, mb);
+        bx = *(volatile unsigned long long*)&mb->speed[par][lane][0];
+        by = *(volatile unsigned long long*)&mb->speed[par][lane][1];
     }
+    if (d.dU_stamp) {        // the two halo stamps are polled by two more lanes meanwhile
+        if (lane == 30 && d.has_lo) spin_until(&mb->halo_stamp[0], d.dU_stamp, mb);
+        if (lane == 31 && d.has_hi) spin_until(&mb->halo_stamp[1], d.dU_stamp, mb);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long tx = __shfl_xor_sync(0xffffffffu, bx, o), ty = __shfl_xor_sync(0xffffffffu, by, o);
+        bx = tx > bx ? tx : bx;
+        by = ty > by ? ty : by;
+    }
+    if (lane != 0) return;
     c->maxspeed_bits[0] = bx;
     c->maxspeed_bits[1] = by;
     const S ax = Bits<S>::dec(bx);
@@ -84,7 +97,7 @@ __device__ __forceinline__ void ctl_dt_multi(Ctl* c, Mailbox* mb, const DtArgs& 
     c->dt = dt;
     c->dt_s = (double)(S)dt;
     if (!past_end) c->dt_report = c->dt_s;
-    if (d.dU_stamp) wait_halo(mb, 0, d.has_lo, d.has_hi, d.dU_stamp);
+    __threadfence_system();
 }
 
 template <class S>
@@ -163,7 +176,7 @@ __global__ void k_halo_push(const PushArgs<S> a) {
     }
     if (a.dt.enabled) {
         __syncthreads();
-        if (threadIdx.x == 0) ctl_dt_multi<S>(a.ctl_rw, a.mbox[a.rank], a.dt);
+        if (threadIdx.x < 32) ctl_dt_multi<S>(a.ctl_rw, a.mbox[a.rank], a.dt);
     }
 }
 
@@ -251,7 +264,9 @@ __global__ void k_tail(const TailArgs<S> a) {
     if (threadIdx.x == 1 && a.push.flag_hi) *(volatile unsigned long long*)a.push.flag_hi = a.push.stamp;
     __syncthreads();
     // the next stage-1 kernel reads the neighbours' rows: wait for them here, at the end of the step's last launch
-    if (threadIdx.x == 0) wait_halo(a.mb, 2, a.has_lo, a.has_hi, a.push.stamp);
+    if (threadIdx.x == 0 && a.has_lo) spin_until(&a.mb->halo_stamp[2], a.push.stamp, a.mb);
+    if (threadIdx.x == 1 && a.has_hi) spin_until(&a.mb->halo_stamp[3], a.push.stamp, a.mb);
+    __threadfence_system();
 }
 
 // ---- device-side rendezvous of all ranks on the handles' streams: every rank announces sequence number `seq` in
