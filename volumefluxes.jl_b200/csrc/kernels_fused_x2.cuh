@@ -145,8 +145,14 @@ __device__ __forceinline__ void recon2(const Par2& p, const f2 c[3], const f2 bw
 #ifndef X2_TCARRY
 #define X2_TCARRY 3          // bit 0: stage 1, bit 1: stage 2 (round 2: stage 1 too, K1 -1.7 %; round 1 it cost registers there)
 #endif
+#ifndef X2_DRYLEAN
+#define X2_DRYLEAN 0         // 1: all-dry warp-rows skip the x reconstruction of the momenta and the flux differences (see the march).
+                             // Bitwise the same results and -18 % / -26 % instructions on a dry row of K2 / K1, but dry rows wait for memory, not
+                             // for issue slots: K1 -1.9 %, K2 +1.8 % on the bench line, +1.6 % with every cell wet (profiles/r03b_ab_diet.txt): off
+#endif
 #ifndef X2_NOGHOST_FAST
-#define X2_NOGHOST_FAST 0    // 1: warps holding x-ghost pairs never take the FAST trips (which then drop the ghost code)
+#define X2_NOGHOST_FAST 0    // 1: warps holding x-ghost pairs never take the FAST trips (which then drop the ghost code): K2 -1.6 .. -2 % at
+                             // 16384^2, +2 % at 8192^2, +13 % at 4096^2 where 2 of 69 tile columns hold ghosts (profiles/r03b_ab_diet.txt): off
 #endif
 template <int RECON>
 __device__ __forceinline__ void recon2t(const Par2& p, const f2 c[3], const f2 tb[3], const f2 fwd[3], f2 tBl, f2 tBr,
@@ -168,18 +174,18 @@ __device__ __forceinline__ void recon2t(const Par2& p, const f2 c[3], const f2 t
 }
 // x direction: the two cells of a thread are neighbours, so the three differences d0 = a - left, d1 = b - a,
 // d2 = right - b are shared; everything is built from scalars that land in aligned pairs (no pair shuffling).
-template <int RECON>
+// (components K0 .. K1 only: the depth (0) decides whether a row's faces are wet; the momenta (1, 2) are only needed if they are)
+template <int RECON, int K0 = 0, int K1 = 2>
 __device__ __forceinline__ void recon2x(const Par2& p, const f2 c[3], const float ql[3], const float qr[3], f2 tBl,
                                         f2 tBr, f2 Bc, f2 L[3], f2 R[3]) {
     if (RECON == 0) {
-        L[0] = R[0] = sub(c[0], Bc);
-        L[1] = R[1] = c[1];
-        L[2] = R[2] = c[2];
+#pragma unroll
+        for (int k = K0; k <= K1; ++k) L[k] = R[k] = k == 0 ? sub(c[0], Bc) : c[k];
         return;
     }
     f2 s[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = K0; k <= K1; ++k) {
         const f2 d01 = mk(c[k].x - ql[k], c[k].y - c[k].x);               // (d0, d1)
         const float d2 = qr[k] - c[k].y;
         const f2 t01 = mul(p.theta, d01);
@@ -187,13 +193,41 @@ __device__ __forceinline__ void recon2x(const Par2& p, const f2 c[3], const floa
         const f2 cen = mul(p.half, mk(c[k].y - ql[k], qr[k] - c[k].x));    // ((d0+d1)/2, (d1+d2)/2)
         s[k] = mk(minmod3f(t01.y, cen.x, t01.x), minmod3f(t2, cen.y, t01.y));
     }
-    faces2(p, c, s, tBl, tBr, L, R);
+    if (K0 == 0 && K1 == 2) { faces2(p, c, s, tBl, tBr, L, R); return; }
+    if (K0 == 0) {                                       // faces2, depth only
+        const f2 w2 = add(c[0], c[0]);
+        const f2 s1 = sub(w2, tBl), s2 = sub(tBr, w2);
+        s[0].x = s[0].x > s1.x ? s1.x : fmaxf(s[0].x, s2.x);
+        s[0].y = s[0].y > s1.y ? s1.y : fmaxf(s[0].y, s2.y);
+    }
+#pragma unroll
+    for (int k = K0; k <= K1; ++k) {
+        L[k] = fma2(s[k], p.mhalf, c[k]);
+        R[k] = fma2(s[k], p.half, c[k]);
+    }
+    if (K0 == 0) {
+        L[0] = fma2(tBl, p.mhalf, L[0]);
+        R[0] = fma2(tBr, p.mhalf, R[0]);
+    }
 }
 
 // desingularised depth of a NON-NEGATIVE depth pair (equation.jl:56-62): max(h, min(h^2/2k + k/2, k)) is
 // h + relu(k - h)^2 / 2k; k - h <= k < 1, so the relu is one saturating add on the FMA pipe.
+// (sub.sat as ONE instruction: nvcc compiles __saturatef(k - h) into FADD + FADD.SAT -- 12 of K2's ~520 instructions per thread-row)
+__device__ __forceinline__ float sub_sat(float a, float b) {
+    float r;
+    asm("sub.sat.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+#ifndef X2_SUBSAT
+#define X2_SUBSAT 1
+#endif
 __device__ __forceinline__ f2 desing_pos2(const Par2& p, f2 h) {
+#if X2_SUBSAT
+    const f2 rl = mk(sub_sat(p.kappa, h.x), sub_sat(p.kappa, h.y));
+#else
     const f2 rl = mk(__saturatef(p.kappa - h.x), __saturatef(p.kappa - h.y));
+#endif
     return fma2(mul(rl, rl), p.i2k, h);
 }
 
@@ -670,13 +704,16 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
             finish_row(fast_tag, remap2, ys2, yflip2, ru, rd, bcell(ty2, ty3), q2);
 
             // ================= reconstruction: row j in x, cell j+1 in y =================
+            // X2_DRYLEAN: the x reconstruction of the momenta (only the x flux reads it) moves into the wet branch, and an all-dry
+            // warp-row finishes without the flux differences (dU = the carried lower y flux: what the zero fluxes add up to)
             f2 Lx[3], Rx[3], Ln[3], tBl, tBr, fwd[3], Ly1[3], Ry1[3];
             constexpr bool TC = (X2_TCARRY >> (STAGE - 1)) & 1;
+            constexpr int KX = X2_DRYLEAN ? 0 : 2;        // last component reconstructed in x before the wet / dry decision
             f2 tfw[3];
+            float ql[3], qr[3];
             {
-                float ql[3], qr[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k <= KX; ++k) {
                     ql[k] = __shfl_up_sync(0xffffffffu, q0[k].y, 1);      // column i-1
                     qr[k] = __shfl_down_sync(0xffffffffu, q0[k].x, 1);    // column i+2
                 }
@@ -684,79 +721,98 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
                     tBl = add(Ej.e, E1.e);
                     tBr = mk(tBl.y, Ej.e2 + E1.e2);
                 } else tBl = tBr = sp(2.0f * p.constB);
-                recon2x<RECON>(p, q0, ql, qr, tBl, tBr, bcell(tyj, ty1), Lx, Rx);
+                recon2x<RECON, 0, KX>(p, q0, ql, qr, tBl, tBr, bcell(tyj, ty1), Lx, Rx);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) Ln[k] = mk(Lx[k].y, __shfl_down_sync(0xffffffffu, Lx[k].x, 1));
+                for (int k = 0; k <= KX; ++k) Ln[k] = mk(Lx[k].y, __shfl_down_sync(0xffffffffu, Lx[k].x, 1));
 #pragma unroll
                 for (int k = 0; k < 3; ++k) fwd[k] = sub(q2[k], q1[k]);
                 if (TC) recon2t<RECON>(p, q1, dprev, fwd, ty1, ty2, bcell(ty1, ty2), Ly1, Ry1, tfw);   // cell j+1
                 else recon2<RECON>(p, q1, dprev, fwd, ty1, ty2, bcell(ty1, ty2), Ly1, Ry1);
             }
-            // ================= fluxes: faces (i|i+1), (i+1|i+2) of row j and face j+1/2 =================
-            // one warp-uniform decision per row: a warp whose x and y faces are all dry skips both evaluations
-            f2 F[3], G[3];
-            const bool wet = any_wet(p, Rx[0], Ln[0]) || any_wet(p, Ry0[0], Ly1[0]);
-            if (__any_sync(0xffffffffu, wet)) {
-                f2 sx, sy;
-                cu2<0, STAGE == 1>(p, Rx, Ln, F, sx);
-                cu2<1, STAGE == 1>(p, Ry0, Ly1, G, sy);
-                if (STAGE == 1 && (FAST || j < jb)) {
-                    if (facea_ok) msx.x = fmaxf(msx.x, sx.x);
-                    if (faceb_ok) msx.y = fmaxf(msx.y, sx.y);
-                    if (out_pair) msy = fmaxf(msy, fmaxf(sy.x, sy.y));
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) F[k] = G[k] = sp(0.0f);
-            }
-            // ================= flux differences, bottom-slope source, per-cell sources =================
-            f2 dU[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float Fp = __shfl_up_sync(0xffffffffu, F[k].y, 1);          // face (i-1 | i)
-                const f2 dF = mk(F[k].x - Fp, F[k].y - F[k].x);
-                // -(1/dy)(G - G_lower) - (1/dx) dF with G_lower carried as (1/dy) G: the carried value dies in the inner fma,
-                // so the new one (end of the row) needs no register copy
-                dU[k] = fma2(p.nrdy, G[k], fma2(p.nrdx, dF, Gl[k]));
-            }
-            if (HASB) {
-                dU[1] = fma2(mul(p.botx, sub(tBr, tBl)), add(Lx[0], Rx[0]), dU[1]);
-                dU[2] = fma2(mul(p.boty, sub(ty1, tyj)), hsy, dU[2]);
-            }
-            dU[0] = add(dU[0], src);
-            if (FACTOR) {
-                const double2 fc = *reinterpret_cast<const double2*>(FAST || j < Ny ? pfac : a.factor);
-                pfac += Nx;
-                dU[0] = fma2(mk((float)fc.x, (float)fc.y), ninfil, dU[0]);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                dprev[k] = (TC && RECON) ? tfw[k] : fwd[k];
-                Ry0[k] = Ry1[k]; Gl[k] = mul(p.prdy, G[k]);
-            }
-            hsy = add(Ly1[0], Ry1[0]);
-            // ================= store =================
-            const bool st = out_pair && (FAST || j < jb);
-            if (STAGE == 1) {
-                if (st) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) st_out(ps + k * planeB, dU[k]);
-                }
-            } else {
-                // rungekutta.jl:39-49 stage 2, then friction (prev = U^1) and the dry clean-up
-                f2 o[3];
+            // ================= flux differences, bottom-slope source, per-cell sources, carries, store =================
+            auto row_tail = [&](auto dry_tag, const f2 F[3], const f2 G[3]) {
+                constexpr bool DRY = decltype(dry_tag)::value;
+                f2 dU[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const f2 un = *reinterpret_cast<const f2*>(smU + uU[0] + R * U_SLOT + k * U_VAR);
-                    o[k] = mul(p.half, add(un, fma2(dt, dU[k], q0[k])));
+                    if (DRY) { dU[k] = Gl[k]; continue; }
+                    const float Fp = __shfl_up_sync(0xffffffffu, F[k].y, 1);          // face (i-1 | i)
+                    const f2 dF = mk(F[k].x - Fp, F[k].y - F[k].x);
+                    // -(1/dy)(G - G_lower) - (1/dx) dF with G_lower carried as (1/dy) G: the carried value dies in the inner fma,
+                    // so the new one (end of the row) needs no register copy
+                    dU[k] = fma2(p.nrdy, G[k], fma2(p.nrdx, dF, Gl[k]));
                 }
-                const f2 fac = tail_factor2<FRIC>(p, q0, bcell(tyj, ty1), czdt, o[0]);
-                o[1] = mul(o[1], fac);
-                o[2] = mul(o[2], fac);
-                if (st) {
+                if (HASB) {
+                    dU[1] = fma2(mul(p.botx, sub(tBr, tBl)), add(Lx[0], Rx[0]), dU[1]);
+                    dU[2] = fma2(mul(p.boty, sub(ty1, tyj)), hsy, dU[2]);
+                }
+                dU[0] = add(dU[0], src);
+                if (FACTOR) {
+                    const double2 fc = *reinterpret_cast<const double2*>(FAST || j < Ny ? pfac : a.factor);
+                    pfac += Nx;
+                    dU[0] = fma2(mk((float)fc.x, (float)fc.y), ninfil, dU[0]);
+                }
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) st_out(ps + k * planeB, o[k]);
+                for (int k = 0; k < 3; ++k) {
+                    dprev[k] = (TC && RECON) ? tfw[k] : fwd[k];
+                    Ry0[k] = Ry1[k]; Gl[k] = DRY ? sp(0.0f) : mul(p.prdy, G[k]);
                 }
+                hsy = add(Ly1[0], Ry1[0]);
+                // ---- store ----
+                const bool st = out_pair && (FAST || j < jb);
+                if (STAGE == 1) {
+                    if (st) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) st_out(ps + k * planeB, dU[k]);
+                    }
+                } else {
+                    // rungekutta.jl:39-49 stage 2, then friction (prev = U^1) and the dry clean-up
+                    f2 o[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const f2 un = *reinterpret_cast<const f2*>(smU + uU[0] + R * U_SLOT + k * U_VAR);
+                        o[k] = mul(p.half, add(un, fma2(dt, dU[k], q0[k])));
+                    }
+                    const f2 fac = tail_factor2<FRIC>(p, q0, bcell(tyj, ty1), czdt, o[0]);
+                    o[1] = mul(o[1], fac);
+                    o[2] = mul(o[2], fac);
+                    if (st) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) st_out(ps + k * planeB, o[k]);
+                    }
+                }
+            };
+            // ================= fluxes: faces (i|i+1), (i+1|i+2) of row j and face j+1/2 =================
+            // one warp-uniform decision per row: a warp whose x and y faces are all dry skips both evaluations
+            const bool wet = any_wet(p, Rx[0], Ln[0]) || any_wet(p, Ry0[0], Ly1[0]);
+            const bool any_w = __any_sync(0xffffffffu, wet);
+            if (X2_DRYLEAN && !any_w) row_tail(std::true_type{}, nullptr, nullptr);
+            else {
+                f2 F[3], G[3];
+                if (any_w) {
+                    if (X2_DRYLEAN) {
+#pragma unroll
+                        for (int k = 1; k < 3; ++k) {
+                            ql[k] = __shfl_up_sync(0xffffffffu, q0[k].y, 1);
+                            qr[k] = __shfl_down_sync(0xffffffffu, q0[k].x, 1);
+                        }
+                        recon2x<RECON, 1, 2>(p, q0, ql, qr, tBl, tBr, bcell(tyj, ty1), Lx, Rx);
+#pragma unroll
+                        for (int k = 1; k < 3; ++k) Ln[k] = mk(Lx[k].y, __shfl_down_sync(0xffffffffu, Lx[k].x, 1));
+                    }
+                    f2 sx, sy;
+                    cu2<0, STAGE == 1>(p, Rx, Ln, F, sx);
+                    cu2<1, STAGE == 1>(p, Ry0, Ly1, G, sy);
+                    if (STAGE == 1 && (FAST || j < jb)) {
+                        if (facea_ok) msx.x = fmaxf(msx.x, sx.x);
+                        if (faceb_ok) msx.y = fmaxf(msx.y, sx.y);
+                        if (out_pair) msy = fmaxf(msy, fmaxf(sy.x, sy.y));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) F[k] = G[k] = sp(0.0f);
+                }
+                row_tail(std::false_type{}, F, G);
             }
             ps += rowB;
             // corner state of the next row
