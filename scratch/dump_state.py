@@ -48,7 +48,9 @@ def main():
     from cases import load_package
     P = load_package()
     res = {}
+    only = sys.argv[2].split(",") if len(sys.argv) > 2 else None      # optional: a comma-separated subset of the case names
     for name, case, state, steps in cases(P):
+        if only and name not in only: continue
         sim = P.simulator_from_case(case, strict=False)
         sim.set_state_interior(*state)
         sim.run_steps(steps)

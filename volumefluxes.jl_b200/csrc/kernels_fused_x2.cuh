@@ -152,7 +152,9 @@ __device__ __forceinline__ void recon2(const Par2& p, const f2 c[3], const f2 bw
 #endif
 #ifndef X2_NOGHOST_FAST
 #define X2_NOGHOST_FAST 0    // 1: warps holding x-ghost pairs never take the FAST trips (which then drop the ghost code): K2 -1.6 .. -2 % at
-                             // 16384^2, +2 % at 8192^2, +13 % at 4096^2 where 2 of 69 tile columns hold ghosts (profiles/r03b_ab_diet.txt): off
+                             // 16384^2, +2 % at 8192^2, +13 % at 4096^2 where 2 of 69 tile columns hold ghosts (profiles/r03b_ab_diet.txt): off.
+                             // 2: K2 carries BOTH FAST flavours and every warp takes the one it needs: bitwise the same results, K2 -2.8 %
+                             // at 16384^2 but +13 % at 4096^2 for the same instantiation (unexplained; profiles/r03b_ab_diet.txt): off
 #endif
 template <int RECON>
 __device__ __forceinline__ void recon2t(const Par2& p, const f2 c[3], const f2 tb[3], const f2 fwd[3], f2 tBl, f2 tBr,
@@ -407,6 +409,10 @@ struct Rings {
     float E2[2][3][NT];
 };
 
+// flavour of a 3-row trip: value = FAST (every fetched row is an interior row), noghost = the warp holds no x-ghost pair either
+template <bool F, bool NG>
+struct TripTag { static constexpr bool value = F; static constexpr bool noghost = NG; };
+
 template <int RECON, bool HASB, int STAGE, int FRIC, bool FACTOR>
 __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
     __shared__ Rings<STAGE> sm;
@@ -481,7 +487,7 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
     const bool xghost = xs != ic;
     // (a FAST trip -- interior rows of a warp without x-ghost pairs -- has nothing to remap, mirror or flip)
     auto finish_row = [&](auto fast_tag, bool remapped, int ys, bool yflip, const f2 u[3], const f2 d[3], f2 Bc_here, f2 q[3]) {
-        constexpr bool FASTROW = X2_NOGHOST_FAST && decltype(fast_tag)::value;
+        constexpr bool FASTROW = decltype(fast_tag)::noghost;
         if (STAGE == 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) q[k] = u[k];
@@ -582,11 +588,11 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
             cp_async4(smE2 + e2bank + slot * E2_SLOT, g + 8);
         }
     };
-    fetch_row(std::false_type{}, ja + 2, 0u, 2);
-    fetch_corner(std::false_type{}, ja + 3, E_BANK, E2_BANK, 0);
+    fetch_row(TripTag<false, false>{}, ja + 2, 0u, 2);
+    fetch_corner(TripTag<false, false>{}, ja + 3, E_BANK, E2_BANK, 0);
     cp_async_commit();
-    fetch_row(std::false_type{}, ja + 3, UB == 2 ? U_BANK : 0u, 0);
-    fetch_corner(std::false_type{}, ja + 4, E_BANK, E2_BANK, 1);
+    fetch_row(TripTag<false, false>{}, ja + 3, UB == 2 ? U_BANK : 0u, 0);
+    fetch_corner(TripTag<false, false>{}, ja + 4, E_BANK, E2_BANK, 1);
     cp_async_commit();
 
     // ---- prologue: state rows ja-2 .. ja+1 and corner rows ja-2 .. ja+2 by direct loads ----
@@ -628,10 +634,10 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
         }
         const f2 tm2 = ty_of(c[0]), tm1 = ty_of(c[1]), t0 = ty_of(c[2]), t1 = ty_of(c[3]), t2 = ty_of(c[4]);
         f2 qa[3], qb[3];
-        finish_row(std::false_type{}, ys[0] != ja - 2, ys[0], yf[0], u[0], d[0], bcell(tm2, tm1), qa);
-        finish_row(std::false_type{}, ys[1] != ja - 1, ys[1], yf[1], u[1], d[1], bcell(tm1, t0), qb);
-        finish_row(std::false_type{}, ys[2] != ja, ys[2], yf[2], u[2], d[2], bcell(t0, t1), q[0]);
-        finish_row(std::false_type{}, ys[3] != ja + 1, ys[3], yf[3], u[3], d[3], bcell(t1, t2), q[1]);
+        finish_row(TripTag<false, false>{}, ys[0] != ja - 2, ys[0], yf[0], u[0], d[0], bcell(tm2, tm1), qa);
+        finish_row(TripTag<false, false>{}, ys[1] != ja - 1, ys[1], yf[1], u[1], d[1], bcell(tm1, t0), qb);
+        finish_row(TripTag<false, false>{}, ys[2] != ja, ys[2], yf[2], u[2], d[2], bcell(t0, t1), q[0]);
+        finish_row(TripTag<false, false>{}, ys[3] != ja + 1, ys[3], yf[3], u[3], d[3], bcell(t1, t2), q[1]);
         f2 b0[3], b1[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -822,8 +828,12 @@ __global__ void __launch_bounds__(NT, minb<STAGE>()) k_stage_x2(const Args2 a) {
         }
     };
     for (int j0 = ja; j0 < jb; j0 += 3, bank ^= 1) {
-        if (j0 + 6 < Ny - 2 && !(X2_NOGHOST_FAST && ghost_warp)) trip(std::true_type{}, j0);
-        else trip(std::false_type{}, j0);
+        if (j0 + 6 < Ny - 2 && !(X2_NOGHOST_FAST == 1 && ghost_warp)) {
+            if (STAGE == 2 && X2_NOGHOST_FAST == 2) {     // two FAST flavours: with the ghost remap / mirror code for the warps that need it
+                if (ghost_warp) trip(TripTag<true, false>{}, j0);
+                else trip(TripTag<true, true>{}, j0);
+            } else trip(TripTag<true, X2_NOGHOST_FAST == 1>{}, j0);
+        } else trip(TripTag<false, false>{}, j0);
     }
     cp_async_wait_all();                                  // the two rows fetched past the chunk: drain before the rings are reused
   }   // work queue
